@@ -1,0 +1,121 @@
+/*
+ * uw_oracle.h -- CPU ORACLE for the UW-SLAM direct photometric tracker.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain C++ restatement of the reference's
+ * algorithm (file:line citations are into /root/reference) used as the parity
+ * checker in tests/, in __graft_entry__.smoke() and as bench.py's cpu_baseline /
+ * --impl reference leg.  Nothing on the product path (uw_slam_b200/, include/)
+ * links, imports or calls it.
+ *
+ * PARITY STATUS: "parity unpinned at the source" -- the reference ships no tests,
+ * golden vectors or fixtures and cannot be compiled here
+ * (needs OpenCV 3.2 C++, Eigen, Ceres, ROS).  Every OpenCV primitive the path
+ * uses is instead pinned bit-for-bit against the real OpenCV (python cv2 4.13)
+ * in tests/test_oracle_vs_cv2.py; the float op order of the few Eigen/Sophus
+ * expressions is a documented canonical choice (docs/ARITHMETIC.md).
+ */
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UWO_MAX_LEVELS 8
+
+/* solve_mode: how `A.inv() * b` (Tracker.cpp:564) is evaluated. */
+#define UWO_SOLVE_LU 0      /* cv::solve(A,b,DECOMP_LU): what OpenCV's MatExpr does */
+#define UWO_SOLVE_INVERSE 1 /* cv::invert(A) then gemm: the literal reading         */
+
+/* accum_mode: accumulator of the normal equations (docs/ARITHMETIC.md U3). */
+#define UWO_ACCUM_DOUBLE 0     /* sequential fp64 (timed baseline)     */
+#define UWO_ACCUM_LONGDOUBLE 1 /* sequential 80-bit (checker, default) */
+
+typedef struct {
+  int width, height;          /* level-0 size; must be divisible by 2^(levels-1) */
+  float fx, fy, cx, cy;       /* level-0 pinhole intrinsics (CameraModel::GetK)   */
+  int levels;                 /* PYRAMID_LEVELS, Options.cpp:26 (5)               */
+  int first_level;            /* Tracker.cpp:368 (levels-1 = 4)                   */
+  int last_level;             /* Tracker.cpp:369 (1)                              */
+  int max_iterations;         /* Tracker.cpp:366 (50)                             */
+  float epsilon;              /* Tracker.cpp:364 (0.001)                          */
+  float residual_scale;       /* Tracker.cpp:559 (50)                             */
+  double gradient_threshold;  /* Options.cpp:27 (20)                              */
+  int solve_mode;             /* UWO_SOLVE_*                                      */
+  int accum_mode;             /* UWO_ACCUM_*                                      */
+  int threads;                /* 1 = like the reference; >1 = std::thread over points  */
+} uwo_params;
+
+/* One record per Gauss-Newton iteration (including the breaking one). */
+typedef struct {
+  int level, k;
+  int n_valid;
+  int broke;                  /* 1 if this iteration hit the break test           */
+  long long sum_r2;           /* exact integer sum of squared residuals           */
+  float error;                /* Tracker.cpp:499-502                              */
+  float A[36];                /* row-major 6x6 (zero when broke)                  */
+  float b[6];
+  float delta[6];
+  float pose[7];              /* pose AFTER this iteration: qx qy qz qw tx ty tz  */
+} uwo_iter_trace;
+
+typedef struct {
+  int iterations[UWO_MAX_LEVELS];   /* GN updates applied per level               */
+  int evaluations[UWO_MAX_LEVELS];  /* residual sweeps per level (= updates + 1)  */
+  int n_points[UWO_MAX_LEVELS];
+  float final_error[UWO_MAX_LEVELS];
+} uwo_stats;
+
+void uwo_default_params(uwo_params* p);
+
+/* System::AddFrame pyramid loop, System.cpp:246-251: exact-half cv::resize. */
+void uwo_pyr_down(const uint8_t* src, int w, int h, uint8_t* dst);
+/* Tracker::ApplyGradient, Tracker.cpp:1133-1134: Scharr 16S, BORDER_REFLECT_101. */
+void uwo_scharr(const uint8_t* img, int w, int h, int16_t* gx, int16_t* gy);
+/* Tracker.cpp:1139-1142: convertScaleAbs x2 + addWeighted(.5,.5). */
+void uwo_gradmag(const int16_t* gx, const int16_t* gy, long long n, uint8_t* g);
+/* Tracker::ObtainCandidatePoints, Tracker.cpp:1314-1357 (mono branch).  pts4 must
+ * hold w*h*4 floats.  Returns the number of candidates; rows are [x,y,1,1], x-major. */
+int uwo_candidates(const uint8_t* g, int w, int h, double gradient_threshold,
+                   float* pts4, double* mean_out, int* ithr_out);
+/* Tracker::InitializePyramid, Tracker.cpp:297-340. Arrays of length `levels`. */
+void uwo_init_pyramid(int w, int h, float fx, float fy, float cx, float cy, int levels,
+                      int* wl, int* hl, float* fxl, float* fyl, float* cxl, float* cyl,
+                      float* invfxl, float* invfyl);
+/* Tracker::WarpFunction, Tracker.cpp:1417-1471. */
+void uwo_warp(const float* pts4, int n, const float* pose7, float fx, float fy, float cx,
+              float cy, float invfx, float invfy, float* out4);
+
+/* Sophus pieces (se3.hpp:723-744, 317-321; so3.hpp:338-355, 434-440, 534-568). */
+void uwo_se3_exp(const float* tangent6, float* pose7);
+void uwo_se3_mul(const float* a7, const float* b7, float* out7);
+void uwo_se3_matrix(const float* pose7, float* m16);
+void uwo_se3_scale_level(const float* pose7, float* out7); /* Tracker.cpp:580-590 */
+
+/* cv::solve / cv::invert (DECOMP_LU) on 6x6 f32.  Return 0 if singular. */
+int uwo_lu_solve6(const float* A36, const float* b6, float* x6);
+int uwo_lu_invert6(const float* A36, float* Ainv36);
+
+/* Whole-frame preprocessing into caller-provided per-level arrays.
+ * images[l]: u8 w_l*h_l (level 0 is input, 1.. are written). */
+void uwo_build_pyramid(const uwo_params* p, uint8_t* const* images);
+
+/* Tracker::EstimatePose, Tracker.cpp:362-597.
+ * prev_images/cur_images/gx/gy: per-level pointers (levels entries);
+ * cand[l]: N_l x 4 f32, ncand[l]: N_l.  init_pose7 may be NULL (identity).
+ * trace may be NULL; at most trace_cap records are written, *n_trace gets the count. */
+int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
+                      const uint8_t* const* cur_images, const int16_t* const* gx,
+                      const int16_t* const* gy, const float* const* cand, const int* ncand,
+                      const float* init_pose7, float* out_pose7, uwo_stats* stats,
+                      uwo_iter_trace* trace, int trace_cap, int* n_trace);
+
+/* Convenience for benchmarks: full track on two level-0 frames (allocates internally):
+ * pyramid(prev), pyramid(cur), ApplyGradient(prev), ObtainCandidatePoints(prev),
+ * EstimatePose(prev,cur).  seconds[0..3] = pyramid, gradient, candidates, estimate. */
+int uwo_track_pair(const uwo_params* p, const uint8_t* prev0, const uint8_t* cur0,
+                   float* out_pose7, uwo_stats* stats, double* seconds4);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,277 @@
+"""ctypes binding of the CPU oracle (oracle/libuw_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference leg.  The product package (uw_slam_b200/) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libuw_oracle.so")
+MAX_LEVELS = 8
+SOLVE_LU, SOLVE_INVERSE = 0, 1
+ACCUM_DOUBLE, ACCUM_LONGDOUBLE = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("levels", C.c_int), ("first_level", C.c_int), ("last_level", C.c_int),
+        ("max_iterations", C.c_int), ("epsilon", C.c_float), ("residual_scale", C.c_float),
+        ("gradient_threshold", C.c_double),
+        ("solve_mode", C.c_int), ("accum_mode", C.c_int), ("threads", C.c_int),
+    ]
+
+
+class IterTrace(C.Structure):
+    _fields_ = [
+        ("level", C.c_int), ("k", C.c_int), ("n_valid", C.c_int), ("broke", C.c_int),
+        ("sum_r2", C.c_longlong), ("error", C.c_float),
+        ("A", C.c_float * 36), ("b", C.c_float * 6), ("delta", C.c_float * 6),
+        ("pose", C.c_float * 7),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int * MAX_LEVELS), ("evaluations", C.c_int * MAX_LEVELS),
+        ("n_points", C.c_int * MAX_LEVELS), ("final_error", C.c_float * MAX_LEVELS),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle with its Makefile (gcc; no GPU needed)."""
+    src = os.path.join(_HERE, "uw_oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        u8p, i16p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_float)
+        L.uwo_default_params.argtypes = [C.POINTER(Params)]
+        L.uwo_pyr_down.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.uwo_scharr.argtypes = [u8p, C.c_int, C.c_int, i16p, i16p]
+        L.uwo_gradmag.argtypes = [i16p, i16p, C.c_longlong, u8p]
+        L.uwo_candidates.argtypes = [u8p, C.c_int, C.c_int, C.c_double, f32p,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.uwo_candidates.restype = C.c_int
+        L.uwo_warp.argtypes = [f32p, C.c_int, f32p] + [C.c_float] * 6 + [f32p]
+        L.uwo_se3_exp.argtypes = [f32p, f32p]
+        L.uwo_se3_mul.argtypes = [f32p, f32p, f32p]
+        L.uwo_se3_matrix.argtypes = [f32p, f32p]
+        L.uwo_se3_scale_level.argtypes = [f32p, f32p]
+        L.uwo_lu_solve6.argtypes = [f32p, f32p, f32p]
+        L.uwo_lu_solve6.restype = C.c_int
+        L.uwo_lu_invert6.argtypes = [f32p, f32p]
+        L.uwo_lu_invert6.restype = C.c_int
+        L.uwo_estimate_pose.restype = C.c_int
+        L.uwo_track_pair.restype = C.c_int
+        L.uwo_track_pair.argtypes = [C.POINTER(Params), u8p, u8p, f32p, C.POINTER(Stats),
+                                     C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def default_params(width=640, height=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, **kw):
+    p = Params()
+    lib().uwo_default_params(C.byref(p))
+    p.width, p.height, p.fx, p.fy, p.cx, p.cy = width, height, fx, fy, cx, cy
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def pyr_down(img):
+    h, w = img.shape
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((h // 2, w // 2), np.uint8)
+    lib().uwo_pyr_down(_p(img, C.c_uint8), w, h, _p(out, C.c_uint8))
+    return out
+
+
+def build_pyramid(img, levels=5):
+    pyr = [np.ascontiguousarray(img, np.uint8)]
+    for _ in range(1, levels):
+        pyr.append(pyr_down(pyr[-1]))
+    return pyr
+
+
+def scharr(img):
+    h, w = img.shape
+    img = np.ascontiguousarray(img, np.uint8)
+    gx = np.empty((h, w), np.int16)
+    gy = np.empty((h, w), np.int16)
+    lib().uwo_scharr(_p(img, C.c_uint8), w, h, _p(gx, C.c_int16), _p(gy, C.c_int16))
+    return gx, gy
+
+
+def gradmag(gx, gy):
+    gx = np.ascontiguousarray(gx, np.int16)
+    gy = np.ascontiguousarray(gy, np.int16)
+    g = np.empty(gx.shape, np.uint8)
+    lib().uwo_gradmag(_p(gx, C.c_int16), _p(gy, C.c_int16), gx.size, _p(g, C.c_uint8))
+    return g
+
+
+def candidates(g, gradient_threshold=20.0):
+    """Returns (N x 4 f32 points in the reference's x-major order, mean, ithr)."""
+    h, w = g.shape
+    g = np.ascontiguousarray(g, np.uint8)
+    pts = np.empty((h * w, 4), np.float32)
+    mean = C.c_double()
+    ithr = C.c_int()
+    n = lib().uwo_candidates(_p(g, C.c_uint8), w, h, gradient_threshold, _p(pts, C.c_float),
+                             C.byref(mean), C.byref(ithr))
+    return pts[:n].copy(), mean.value, ithr.value
+
+
+def init_pyramid(w, h, fx, fy, cx, cy, levels=5):
+    wl = (C.c_int * levels)()
+    hl = (C.c_int * levels)()
+    arrs = [(C.c_float * levels)() for _ in range(6)]
+    L = lib()
+    L.uwo_init_pyramid.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + \
+        [C.POINTER(C.c_int)] * 2 + [C.POINTER(C.c_float)] * 6
+    L.uwo_init_pyramid(w, h, fx, fy, cx, cy, levels, wl, hl, *arrs)
+    names = ["fx", "fy", "cx", "cy", "invfx", "invfy"]
+    out = {"w": list(wl), "h": list(hl)}
+    for nme, a in zip(names, arrs):
+        out[nme] = np.array(list(a), np.float32)
+    return out
+
+
+def warp(pts4, pose7, fx, fy, cx, cy, invfx, invfy):
+    pts4 = np.ascontiguousarray(pts4, np.float32)
+    pose7 = np.ascontiguousarray(pose7, np.float32)
+    out = np.empty_like(pts4)
+    lib().uwo_warp(_p(pts4, C.c_float), pts4.shape[0], _p(pose7, C.c_float),
+                   fx, fy, cx, cy, invfx, invfy, _p(out, C.c_float))
+    return out
+
+
+def se3_exp(t6):
+    t6 = np.ascontiguousarray(t6, np.float32)
+    o = np.empty(7, np.float32)
+    lib().uwo_se3_exp(_p(t6, C.c_float), _p(o, C.c_float))
+    return o
+
+
+def se3_mul(a7, b7):
+    a7 = np.ascontiguousarray(a7, np.float32)
+    b7 = np.ascontiguousarray(b7, np.float32)
+    o = np.empty(7, np.float32)
+    lib().uwo_se3_mul(_p(a7, C.c_float), _p(b7, C.c_float), _p(o, C.c_float))
+    return o
+
+
+def se3_matrix(p7):
+    p7 = np.ascontiguousarray(p7, np.float32)
+    o = np.empty(16, np.float32)
+    lib().uwo_se3_matrix(_p(p7, C.c_float), _p(o, C.c_float))
+    return o.reshape(4, 4)
+
+
+def se3_scale_level(p7):
+    p7 = np.ascontiguousarray(p7, np.float32)
+    o = np.empty(7, np.float32)
+    lib().uwo_se3_scale_level(_p(p7, C.c_float), _p(o, C.c_float))
+    return o
+
+
+def lu_solve6(A, b):
+    A = np.ascontiguousarray(A, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    x = np.empty(6, np.float32)
+    ok = lib().uwo_lu_solve6(_p(A, C.c_float), _p(b, C.c_float), _p(x, C.c_float))
+    return x, ok
+
+
+def lu_invert6(A):
+    A = np.ascontiguousarray(A, np.float32)
+    Ai = np.empty((6, 6), np.float32)
+    ok = lib().uwo_lu_invert6(_p(A, C.c_float), _p(Ai, C.c_float))
+    return Ai, ok
+
+
+class FrameData:
+    """What uw::Frame holds after pyramid + ApplyGradient + ObtainCandidatePoints."""
+
+    def __init__(self, img, levels=5, gradient_threshold=20.0, with_candidates=True):
+        self.images = build_pyramid(img, levels)
+        self.gx, self.gy, self.g, self.cand, self.mean, self.ithr = [], [], [], [], [], []
+        if with_candidates:
+            for im in self.images:
+                gx, gy = scharr(im)
+                g = gradmag(gx, gy)
+                c, m, t = candidates(g, gradient_threshold)
+                self.gx.append(gx)
+                self.gy.append(gy)
+                self.g.append(g)
+                self.cand.append(c)
+                self.mean.append(m)
+                self.ithr.append(t)
+
+
+def estimate_pose(params, prev, cur, init_pose=None, trace_cap=256):
+    """Tracker::EstimatePose on two FrameData.  Returns (pose7, Stats, [IterTrace])."""
+    L = params.levels
+    u8pp = (C.POINTER(C.c_uint8) * MAX_LEVELS)
+    i16pp = (C.POINTER(C.c_int16) * MAX_LEVELS)
+    f32pp = (C.POINTER(C.c_float) * MAX_LEVELS)
+    pi, ci, gx, gy, cd = u8pp(), u8pp(), i16pp(), i16pp(), f32pp()
+    nc = (C.c_int * MAX_LEVELS)()
+    keep = []
+    for l in range(L):
+        a = np.ascontiguousarray(prev.images[l]); keep.append(a); pi[l] = _p(a, C.c_uint8)
+        a = np.ascontiguousarray(cur.images[l]); keep.append(a); ci[l] = _p(a, C.c_uint8)
+        a = np.ascontiguousarray(prev.gx[l]); keep.append(a); gx[l] = _p(a, C.c_int16)
+        a = np.ascontiguousarray(prev.gy[l]); keep.append(a); gy[l] = _p(a, C.c_int16)
+        a = np.ascontiguousarray(prev.cand[l], np.float32); keep.append(a)
+        cd[l] = _p(a, C.c_float)
+        nc[l] = a.shape[0]
+    out = np.empty(7, np.float32)
+    st = Stats()
+    tr = (IterTrace * trace_cap)()
+    ntr = C.c_int(0)
+    ip = None
+    if init_pose is not None:
+        ipa = np.ascontiguousarray(init_pose, np.float32)
+        keep.append(ipa)
+        ip = _p(ipa, C.c_float)
+    rc = lib().uwo_estimate_pose(C.byref(params), pi, ci, gx, gy, cd, nc, ip,
+                                 _p(out, C.c_float), C.byref(st), tr, trace_cap, C.byref(ntr))
+    if rc != 0:
+        raise RuntimeError("uwo_estimate_pose failed: %d" % rc)
+    return out, st, [tr[i] for i in range(ntr.value)]
+
+
+def track_pair(params, prev0, cur0):
+    """Full track (pyramids, gradient, candidates, estimate).  Returns (pose7, Stats, secs[4])."""
+    prev0 = np.ascontiguousarray(prev0, np.uint8)
+    cur0 = np.ascontiguousarray(cur0, np.uint8)
+    out = np.empty(7, np.float32)
+    st = Stats()
+    secs = (C.c_double * 4)()
+    rc = lib().uwo_track_pair(C.byref(params), _p(prev0, C.c_uint8), _p(cur0, C.c_uint8),
+                              _p(out, C.c_float), C.byref(st), secs)
+    if rc != 0:
+        raise RuntimeError("uwo_track_pair failed: %d" % rc)
+    return out, st, list(secs)

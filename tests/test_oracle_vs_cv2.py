@@ -1,0 +1,166 @@
+"""Pins the CPU oracle's OpenCV primitives bit-for-bit against the real OpenCV (cv2).
+
+The reference has no tests or golden vectors, and its OpenCV 3.2
+C++ build cannot be reproduced here; python cv2 runs the same core/imgproc algorithms, so
+every primitive on the hot path is checked against it.  CPU only.
+"""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+SIZES = [(64, 48), (160, 128), (640, 480), (752, 480), (1280, 1024)]
+
+
+def rand_img(rng, w, h, smooth=False):
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if smooth:
+        img = cv2.GaussianBlur(img, (0, 0), 2.0)
+    return img
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(3840, 2160)])
+def test_pyr_down_matches_cv_resize(oracle, w, h):
+    # System.cpp:247: resize(prev, next, Size(), 0.5, 0.5) (default INTER_LINEAR)
+    rng = np.random.default_rng(w * 7 + h)
+    img = rand_img(rng, w, h)
+    ref = cv2.resize(img, None, fx=0.5, fy=0.5)
+    assert np.array_equal(oracle.pyr_down(img), ref)
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_scharr_matches_cv(oracle, w, h):
+    # Tracker.cpp:1133-1134
+    rng = np.random.default_rng(w + h)
+    img = rand_img(rng, w, h)
+    gx, gy = oracle.scharr(img)
+    assert np.array_equal(gx, cv2.Scharr(img, cv2.CV_16S, 1, 0, scale=1, delta=0,
+                                         borderType=cv2.BORDER_DEFAULT))
+    assert np.array_equal(gy, cv2.Scharr(img, cv2.CV_16S, 0, 1, scale=1, delta=0,
+                                         borderType=cv2.BORDER_DEFAULT))
+
+
+def test_gradmag_exhaustive(oracle):
+    # Tracker.cpp:1139-1142: convertScaleAbs x2 then addWeighted(.5,.5,0); all |g| pairs
+    v = np.arange(-300, 301, dtype=np.int16)
+    gx, gy = np.meshgrid(v, v)
+    gx = np.ascontiguousarray(gx)
+    gy = np.ascontiguousarray(gy)
+    ref = cv2.addWeighted(cv2.convertScaleAbs(gx, alpha=1.0, beta=0.0), 0.5,
+                          cv2.convertScaleAbs(gy, alpha=1.0, beta=0.0), 0.5, 0)
+    assert np.array_equal(oracle.gradmag(gx, gy), ref)
+    big = np.array([[4080, -4080, 255, -256]], np.int16)
+    ref = cv2.addWeighted(cv2.convertScaleAbs(big), 0.5, cv2.convertScaleAbs(big[:, ::-1].copy()),
+                          0.5, 0)
+    assert np.array_equal(oracle.gradmag(big, big[:, ::-1].copy()), ref)
+
+
+@pytest.mark.parametrize("w,h", SIZES[:4])
+def test_candidates_match_cv(oracle, w, h):
+    # Tracker.cpp:1325-1357: meanStdDev, thres = mean + 20 (float), threshold, x-major scan
+    rng = np.random.default_rng(w * 3 + h)
+    img = rand_img(rng, w, h, smooth=True)
+    gx, gy = oracle.scharr(img)
+    g = oracle.gradmag(gx, gy)
+    pts, mean, ithr = oracle.candidates(g, 20.0)
+    m, _ = cv2.meanStdDev(g)
+    thres = np.float32(m[0, 0] + 20.0)
+    _, filt = cv2.threshold(g, float(thres), 255, cv2.THRESH_BINARY)
+    xs, ys = np.nonzero(filt.T)  # transposed: x outer, y inner
+    ref = np.stack([xs, ys, np.ones_like(xs), np.ones_like(xs)], 1).astype(np.float32)
+    assert abs(mean - m[0, 0]) <= 1e-12 * max(1.0, mean)
+    assert pts.shape == ref.shape and np.array_equal(pts, ref)
+    assert 0 < pts.shape[0] < w * h
+
+
+def test_threshold_floors_float_threshold(oracle):
+    g = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    for thr in [20.0, 20.4, 20.999, 147.5 - 20.0]:
+        _, filt = cv2.threshold(g, float(np.float32(127.5 + thr)), 255, cv2.THRESH_BINARY)
+        pts, mean, ithr = oracle.candidates(g, thr)
+        assert mean == 127.5
+        assert pts.shape[0] == int(np.count_nonzero(filt))
+
+
+def cond_matrix(rng):
+    # J^T J-like SPD matrices with the wide dynamic range of the tracker's normal equations
+    J = rng.normal(size=(400, 6)) * np.array([50, 50, 3e3, 4e5, 4e5, 2e4])
+    A = (J.T @ J).astype(np.float32)
+    b = (J.T @ rng.normal(size=400) * 50).astype(np.float32)
+    return A, b
+
+
+def test_lu_solve_matches_cv_solve(oracle):
+    # Tracker.cpp:564: A.inv()*b is folded by cv::MatExpr into cv::solve(A,b,DECOMP_LU)
+    rng = np.random.default_rng(5)
+    for i in range(300):
+        A, b = cond_matrix(rng) if i % 2 else (rng.normal(size=(6, 6)).astype(np.float32),
+                                               rng.normal(size=6).astype(np.float32))
+        ok, ref = cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_LU)
+        x, ok2 = oracle.lu_solve6(A, b)
+        assert bool(ok) == bool(ok2)
+        assert np.array_equal(x, ref.ravel()), i
+
+
+def test_lu_invert_matches_cv_invert(oracle):
+    rng = np.random.default_rng(6)
+    for i in range(300):
+        A = cond_matrix(rng)[0] if i % 2 else rng.normal(size=(6, 6)).astype(np.float32)
+        _, ref = cv2.invert(A, flags=cv2.DECOMP_LU)
+        Ai, ok = oracle.lu_invert6(A)
+        assert ok == 1
+        assert np.array_equal(Ai, ref), i
+
+
+def test_lu_singular_gives_zero(oracle):
+    A = np.zeros((6, 6), np.float32)
+    A[0, 0] = 1.0
+    b = np.ones(6, np.float32)
+    ok, ref = cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_LU)
+    x, ok2 = oracle.lu_solve6(A, b)
+    assert not ok and ok2 == 0 and np.all(x == 0) and np.all(ref == 0)
+    Ai, ok3 = oracle.lu_invert6(A)
+    r, refi = cv2.invert(A, flags=cv2.DECOMP_LU)
+    assert ok3 == 0 and r == 0.0 and np.all(Ai == 0) and np.all(refi == 0)
+
+
+def test_warp_matches_cv_gemm(oracle):
+    # Tracker.cpp:1417-1471 with the 4x4 * (N x 4)^T product done by the real cv2.gemm
+    rng = np.random.default_rng(11)
+    K = oracle.init_pyramid(640, 480, 525.0, 525.0, 319.5, 239.5, 5)
+    for lvl in [1, 4]:
+        w, h = K["w"][lvl], K["h"][lvl]
+        n = 20000
+        pts = np.ones((n, 4), np.float32)
+        pts[:, 0] = rng.integers(0, w, n)
+        pts[:, 1] = rng.integers(0, h, n)
+        pose = oracle.se3_exp(np.array([4e-3, -3e-3, 2e-3, 2e-3, -3e-3, 4e-3], np.float32))
+        fx, fy, cx, cy = (K[k][lvl] for k in ("fx", "fy", "cx", "cy"))
+        ifx, ify = K["invfx"][lvl], K["invfy"][lvl]
+        out = oracle.warp(pts, pose, fx, fy, cx, cy, ifx, ify)
+        P = pts.copy()
+        P[:, 0] = ((P[:, 0] - cx) * ifx) * P[:, 2]
+        P[:, 1] = ((P[:, 1] - cy) * ify) * P[:, 2]
+        T = oracle.se3_matrix(pose)
+        D = cv2.gemm(T, P, 1.0, None, 0.0, flags=cv2.GEMM_2_T)
+        D[0] = cv2.divide(D[0] * fx, D[2]).ravel() + cx
+        D[1] = cv2.divide(D[1] * fy, D[2]).ravel() + cy
+        D[0] *= D[3]
+        D[1] *= D[3]
+        assert np.array_equal(out, D.T)
+
+
+def test_init_pyramid_matches_source_formulas(oracle):
+    # Tracker.cpp:297-340 evaluated with numpy scalars of the same widths
+    for (w, h, fx, fy, cx, cy) in [(640, 480, 525.0, 525.0, 319.5, 239.5),
+                                   (752, 480, 458.654, 457.296, 367.215, 248.375),
+                                   (1280, 1024, 685.72, 685.64, 630.86, 511.92)]:
+        K = oracle.init_pyramid(w, h, fx, fy, cx, cy, 5)
+        f = np.float32
+        efx, ecx = f(fx), f(cx)
+        for l in range(1, 5):
+            efx = f(np.float64(efx) * 0.5)
+            ecx = f((np.float64(f(cx)) + 0.5) / (1 << l) - 0.5)
+            assert K["fx"][l] == efx and K["cx"][l] == ecx
+            assert K["invfx"][l] == f(1) / efx
+            assert K["w"][l] == w >> l and K["h"][l] == h >> l
