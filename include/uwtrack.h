@@ -1,0 +1,158 @@
+/*
+ * uwtrack.h -- C ABI of the B200-native direct photometric tracker (libuwtrack.so).
+ *
+ * Drop-in boundary for the hot path of MecatronicaUSB/uw-slam: the calls `uw::System`
+ * makes on `uw::Tracker` for the direct (photometric) tracker, plus the pyramid loop of
+ * `System::AddFrame`.  Citations are file:line into the reference tree.
+ *
+ *   reference interface                                        replaced by
+ *   ---------------------------------------------------------  --------------------------
+ *   Tracker::Tracker(bool)              include/Tracker.h:97    uwt_create
+ *   Tracker::InitializePyramid(w,h,K)   include/Tracker.h:112   uwt_create (cfg intrinsics),
+ *                                       src/Tracker.cpp:297     uwt_get_level_info
+ *   System::AddFrame pyramid loop       src/System.cpp:246-251  uwt_upload_frames,
+ *                                                               uwt_set_frames_device
+ *   Tracker::ApplyGradient(Frame*)      include/Tracker.h:137   uwt_apply_gradient
+ *   Tracker::ObtainCandidatePoints(F*)  include/Tracker.h:145   uwt_select_candidates
+ *   Tracker::EstimatePose(F*,F*)        include/Tracker.h:122   uwt_estimate_pose
+ *   Tracker::WarpFunction(Mat,SE3,int)  include/Tracker.h:193   uwt_warp_points
+ *   uw::Frame members (images_, gradientX_, gradientY_,        uwt_get_image, uwt_get_gradients,
+ *     gradient_, candidatePoints_)      include/System.h:63-103 uwt_get_candidates
+ *
+ * Conventions: every call returns 0 on success or a negative UWT_E_* code and never
+ * exits, aborts or prints; the caller owns host buffers, the library owns device memory;
+ * a pose is 7 floats in Sophus storage order [qx qy qz qw tx ty tz]
+ * (thirdparty/sophus/se3.hpp:469-472); one handle = one CUDA device + one stream; calls on
+ * one handle must be serialised by the caller, different handles may be used concurrently.
+ * A "slot" is the device-side storage of one uw::Frame.  All array calls take `n` slots so
+ * that n independent tracking problems are processed by one set of kernel launches.
+ * There is no CPU fallback: every entry point fails with UWT_E_CUDA if no device is usable.
+ */
+#ifndef UWTRACK_H_
+#define UWTRACK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UWT_MAX_LEVELS 7
+
+#define UWT_OK 0
+#define UWT_E_INVALID (-1) /* bad argument / unsupported configuration */
+#define UWT_E_CUDA (-2)    /* CUDA runtime error (see uwt_last_error)   */
+#define UWT_E_STATE (-3)   /* call order violated (e.g. no gradients)   */
+#define UWT_E_NOMEM (-4)
+
+/* How `deltaMat = A.inv() * b` (src/Tracker.cpp:564) is evaluated. */
+#define UWT_SOLVE_LU 0      /* cv::solve(A, b, DECOMP_LU) -- what cv::MatExpr folds it to */
+#define UWT_SOLVE_INVERSE 1 /* cv::invert(A, DECOMP_LU) followed by the 6x6 * 6x1 gemm    */
+
+/* cfg.flags */
+#define UWT_FLAG_TRACE 1u /* record a per-iteration trace (uwt_get_trace); debugging/parity */
+
+typedef struct uwt_tracker uwt_tracker;
+
+typedef struct {
+  int width, height;         /* level-0 size, divisible by 2^(levels-1)                  */
+  float fx, fy, cx, cy;      /* CameraModel::GetK(), src/CameraModel.cpp:113-115         */
+  int levels;                /* PYRAMID_LEVELS, src/Options.cpp:26 (5)                   */
+  int first_level;           /* src/Tracker.cpp:368 (levels-1)                           */
+  int last_level;            /* src/Tracker.cpp:369 (1)                                  */
+  int max_iterations;        /* src/Tracker.cpp:366 (50)                                 */
+  float epsilon;             /* src/Tracker.cpp:364 (0.001)                              */
+  float residual_scale;      /* src/Tracker.cpp:559 (50)                                 */
+  double gradient_threshold; /* GRADIENT_THRESHOLD, src/Options.cpp:27 (20)              */
+  int solve_mode;            /* UWT_SOLVE_*                                              */
+  int device;                /* CUDA device ordinal                                      */
+  int max_frames;            /* number of frame slots to allocate                        */
+  int cluster_size;          /* CTAs cooperating on ONE problem in uwt_estimate_pose:
+                                0 = choose from n (1 for large batches, 16 for n == 1)   */
+  unsigned flags;            /* UWT_FLAG_*                                               */
+} uwt_config;
+
+typedef struct {
+  int width, height;
+  float fx, fy, cx, cy, invfx, invfy;
+} uwt_level_info;
+
+typedef struct {
+  int iterations[UWT_MAX_LEVELS];  /* Gauss-Newton updates applied per level         */
+  int evaluations[UWT_MAX_LEVELS]; /* residual sweeps per level                      */
+  int n_points[UWT_MAX_LEVELS];    /* candidate points used per level                */
+  float final_error[UWT_MAX_LEVELS];
+} uwt_track_stats;
+
+/* Same content as the oracle's trace record, one per residual sweep. */
+typedef struct {
+  int level, k, n_valid, broke;
+  long long sum_r2;
+  float error;
+  float A[36];
+  float b[6];
+  float delta[6];
+  float pose[7];
+} uwt_iter_trace;
+
+/* Fills cfg with the reference's defaults (640x480 TUM calibration, 5/4/1 levels). */
+int uwt_default_config(uwt_config* cfg);
+/* Tracker::Tracker + Tracker::InitializePyramid.  On failure *out is NULL and the message
+ * is available from uwt_last_error(NULL). */
+int uwt_create(const uwt_config* cfg, uwt_tracker** out);
+int uwt_destroy(uwt_tracker* t);
+/* Message of the last failure on this handle (t == NULL: of the last uwt_create). */
+const char* uwt_last_error(const uwt_tracker* t);
+/* Per-level geometry and intrinsics computed as in src/Tracker.cpp:297-340. */
+int uwt_get_level_info(const uwt_tracker* t, int level, uwt_level_info* info);
+/* The CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
+void* uwt_stream(const uwt_tracker* t);
+int uwt_synchronize(uwt_tracker* t);
+
+/* System::AddFrame: copy n gray frames from HOST memory (frame i at host + i*frame_stride,
+ * rows row_stride bytes apart) into slots[i] and build their pyramids.  Asynchronous with
+ * respect to the host when `host` is pinned; resets the slots' gradient/candidate state. */
+int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* host,
+                      size_t row_stride, size_t frame_stride);
+/* Same, from frames already resident in DEVICE memory. */
+int uwt_set_frames_device(uwt_tracker* t, int n, const int* slots, const uint8_t* dev,
+                          size_t row_stride, size_t frame_stride);
+/* Tracker::ApplyGradient for n slots: gradientX_, gradientY_ (int16) and gradient_ (u8) on
+ * every pyramid level. */
+int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots);
+/* Tracker::ObtainCandidatePoints for n slots (needs gradients): candidatePoints_ on every
+ * level, in the reference's x-major order. */
+int uwt_select_candidates(uwt_tracker* t, int n, const int* slots);
+/* Tracker::EstimatePose for n independent (prev, cur) pairs.  prev slots need candidates,
+ * cur slots need a pyramid.  init_poses7 (n*7 floats) may be NULL = identity, which is the
+ * reference (src/Tracker.cpp:385).  out_poses7 (n*7 floats, host) receives
+ * prev->rigid_transformation_; stats (n entries, host) may be NULL.  Synchronous. */
+int uwt_estimate_pose(uwt_tracker* t, int n, const int* prev_slots, const int* cur_slots,
+                      const float* init_poses7, float* out_poses7, uwt_track_stats* stats);
+/* Asynchronous form: results land in library-owned pinned memory after uwt_synchronize;
+ * fetch them with uwt_fetch_poses.  Lets the host overlap uploads with tracking. */
+int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots,
+                            const int* cur_slots, const float* init_poses7);
+int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* stats);
+/* Tracker::WarpFunction on host points (n x 4 floats [x y Z W]) at a pyramid level. */
+int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,
+                    float* out4);
+
+/* Read-back accessors (uw::Frame members), dense row-major host buffers. */
+int uwt_get_image(uwt_tracker* t, int slot, int level, uint8_t* host);
+int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t* gy,
+                      uint8_t* g);
+int uwt_get_candidate_count(uwt_tracker* t, int slot, int level, int* n);
+/* candidatePoints_[level] as the reference stores it: rows [x, y, 1, 1] (CV_32FC1). */
+int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int capacity_rows,
+                       int* n);
+/* Trace of problem `index` of the last uwt_estimate_pose (needs UWT_FLAG_TRACE). */
+int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, int* n);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+long long uwt_launch_count(const uwt_tracker* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWTRACK_H_ */

@@ -369,10 +369,13 @@ void uwo_warp(const float* pts4, int n, const float* pose7, float fx, float fy, 
     const float Y = ((y - cy) * invfy) * Z;  // Tracker.cpp:1443-1444
     // rigid * points.t() (Tracker.cpp:1450) is cv::gemm(GEMM_2_T): double accumulators,
     // one rounding to f32 (verified against cv2.gemm, tests/test_oracle_vs_cv2.py).
+    // Products of f32-valued doubles are exact, so the association below only moves
+    // roundings at the 1e-16 level; this order is the canonical one (ARITHMETIC.md U4).
     float o[4];
     for (int r = 0; r < 4; ++r)
-      o[r] = (float)(T[r * 4 + 0] * (double)X + T[r * 4 + 1] * (double)Y +
-                     T[r * 4 + 2] * (double)Z + T[r * 4 + 3] * (double)W);
+      o[r] = (float)(T[r * 4 + 0] * (double)X +
+                     (T[r * 4 + 1] * (double)Y +
+                      (T[r * 4 + 2] * (double)Z + T[r * 4 + 3] * (double)W)));
     // Tracker.cpp:1454-1467; cv::divide yields 0 for a zero divisor
     const float qx = (o[2] != 0.0f) ? (o[0] * fx) / o[2] : 0.0f;
     const float qy = (o[2] != 0.0f) ? (o[1] * fy) / o[2] : 0.0f;

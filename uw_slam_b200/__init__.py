@@ -1,0 +1,8 @@
+"""uw_slam_b200 -- B200-native direct photometric tracker (hot path of uw-slam's Tracker).
+
+The compute lives in libuwtrack.so (hand-written CUDA for sm_100a behind the C ABI of
+include/uwtrack.h); this package is the thin host-side mirror of the reference's
+Tracker / CameraModel / Frame surface plus the synthetic-input generator.
+"""
+from .tracker import CameraModel, Frame, Tracker, UwtError  # noqa: F401
+from . import synth  # noqa: F401

@@ -1,0 +1,679 @@
+// uwt_api.cu -- host side of the C ABI declared in include/uwtrack.h.
+//
+// Owns the device memory pools (one "slot" per uw::Frame), the per-level geometry and
+// intrinsics (Tracker::InitializePyramid, /root/reference/src/Tracker.cpp:297-340), a ring
+// of pinned argument buffers, and enqueues the kernels of the hot path on one stream.
+// There is no CPU fallback anywhere in this file: without a usable CUDA device every entry
+// point returns UWT_E_CUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "uwt_internal.cuh"
+
+using namespace uwt;
+
+namespace {
+
+constexpr int kRing = 8;
+constexpr int kTraceProblems = 64;
+
+thread_local std::string g_create_error;
+
+struct SlotState {
+  bool pyramid = false, gradient = false, candidates = false;
+};
+
+struct ArgRegion {
+  int* h_int = nullptr;      // pinned: [2 * max_frames]
+  float* h_flt = nullptr;    // pinned: [7 * max_frames]
+  int* d_int = nullptr;
+  float* d_flt = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+};
+
+}  // namespace
+
+struct uwt_tracker {
+  uwt_config cfg;
+  Geom geom;
+  Pools pools;
+  cudaStream_t stream = nullptr;
+  std::vector<SlotState> slots;
+  ArgRegion ring[kRing];
+  int ring_next = 0;
+  uint8_t* d_stage = nullptr;  // upload staging
+  size_t stage_frames = 0;
+  float* d_out_poses = nullptr;
+  uwt_track_stats* d_stats = nullptr;
+  float* h_out_poses = nullptr;       // pinned
+  uwt_track_stats* h_stats = nullptr; // pinned
+  uwt_iter_trace* d_trace = nullptr;
+  int* d_trace_count = nullptr;
+  int trace_cap = 0;
+  int last_n = 0;
+  int max_cluster = 1;
+  long long launches = 0;
+  std::string error;
+};
+
+namespace {
+
+int fail(uwt_tracker* t, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (t)
+    t->error = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define UWT_CUDA(t, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail((t), UWT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int build_geom(const uwt_config& c, Geom& g) {
+  std::memset(&g, 0, sizeof(g));
+  g.levels = c.levels;
+  g.first_level = c.first_level;
+  g.last_level = c.last_level;
+  g.max_iterations = c.max_iterations;
+  g.epsilon = c.epsilon;
+  g.residual_scale = c.residual_scale;
+  g.gradient_threshold = c.gradient_threshold;
+  g.solve_mode = c.solve_mode;
+  size_t plane = 0, cand = 0, rec = 0, cnt = 0;
+  int tiles = 0, items = 0;
+  // Tracker::InitializePyramid, Tracker.cpp:297-340 (same expression types as the source:
+  // float members, double literals)
+  float fx[kMaxLevels], fy[kMaxLevels], cx[kMaxLevels], cy[kMaxLevels];
+  fx[0] = c.fx; fy[0] = c.fy; cx[0] = c.cx; cy[0] = c.cy;
+  for (int l = 0; l < c.levels; ++l) {
+    LevelGeom& L = g.lv[l];
+    if (l > 0) {
+      fx[l] = fx[l - 1] * 0.5;
+      fy[l] = fy[l - 1] * 0.5;
+      cx[l] = (cx[0] + 0.5) / ((int)1 << l) - 0.5;
+      cy[l] = (cy[0] + 0.5) / ((int)1 << l) - 0.5;
+    }
+    L.w = c.width >> l;
+    L.h = c.height >> l;
+    L.pitch = (int)align_up((size_t)L.w, 16);
+    L.fx = fx[l]; L.fy = fy[l]; L.cx = cx[l]; L.cy = cy[l];
+    L.invfx = 1 / fx[l];
+    L.invfy = 1 / fy[l];
+    L.plane_off = (int)plane;
+    plane += align_up((size_t)L.pitch * L.h, 256);
+    L.cand_off = (int)cand;
+    cand += align_up((size_t)L.w * L.h, 64);
+    if (l >= c.last_level && l <= c.first_level) {
+      L.rec_off = (int)rec;
+      rec += align_up((size_t)L.w * L.h, 64);
+    } else {
+      L.rec_off = -1;
+    }
+    L.nstrip = (L.w + kStripW - 1) / kStripW;
+    L.nseg = (L.h + kSegRows - 1) / kSegRows;
+    L.cnt_off = (int)cnt;
+    cnt += align_up((size_t)L.w * L.nseg, 64);
+    L.tiles_x = (L.w + kGradTileW - 1) / kGradTileW;
+    L.tiles_y = (L.h + kGradTileH - 1) / kGradTileH;
+    L.tile_off = tiles;
+    tiles += L.tiles_x * L.tiles_y;
+    items += L.nstrip * L.nseg;
+  }
+  g.plane_elems = plane;
+  g.cand_elems = cand;
+  g.rec_elems = rec ? rec : 64;
+  g.cnt_elems = cnt;
+  g.tile_elems = align_up((size_t)tiles, 64);
+  g.grad_tiles_total = tiles;
+  g.warp_items_total = items;
+  return 0;
+}
+
+int check_slots(uwt_tracker* t, int n, const int* slots) {
+  if (!t) return UWT_E_INVALID;
+  if (n <= 0 || n > t->cfg.max_frames || !slots)
+    return fail(t, UWT_E_INVALID, "n=%d out of range (1..%d) or slots NULL", n, t->cfg.max_frames);
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= t->cfg.max_frames)
+      return fail(t, UWT_E_INVALID, "slot %d out of range (0..%d)", slots[i], t->cfg.max_frames - 1);
+  return UWT_OK;
+}
+
+// Acquire the next argument region (waits only if the GPU is kRing calls behind).
+int acquire(uwt_tracker* t, ArgRegion** out) {
+  ArgRegion& r = t->ring[t->ring_next];
+  t->ring_next = (t->ring_next + 1) % kRing;
+  if (r.pending) {
+    UWT_CUDA(t, cudaEventSynchronize(r.ev));
+    r.pending = false;
+  }
+  *out = &r;
+  return UWT_OK;
+}
+
+int release(uwt_tracker* t, ArgRegion* r) {
+  UWT_CUDA(t, cudaEventRecord(r->ev, t->stream));
+  r->pending = true;
+  return UWT_OK;
+}
+
+int push_slots(uwt_tracker* t, ArgRegion* r, int n, const int* a, const int* b) {
+  std::memcpy(r->h_int, a, sizeof(int) * n);
+  if (b) std::memcpy(r->h_int + n, b, sizeof(int) * n);
+  UWT_CUDA(t, cudaMemcpyAsync(r->d_int, r->h_int, sizeof(int) * n * (b ? 2 : 1),
+                              cudaMemcpyHostToDevice, t->stream));
+  return UWT_OK;
+}
+
+void destroy_impl(uwt_tracker* t) {
+  if (!t) return;
+  cudaSetDevice(t->cfg.device);
+  if (t->stream) cudaStreamSynchronize(t->stream);
+  Pools& p = t->pools;
+  cudaFree(p.img); cudaFree(p.gx); cudaFree(p.gy); cudaFree(p.g); cudaFree(p.gpart);
+  cudaFree(p.ticket); cudaFree(p.ithr); cudaFree(p.cnt); cudaFree(p.ncand);
+  cudaFree(p.cand_xy); cudaFree(p.rec);
+  for (ArgRegion& r : t->ring) {
+    if (r.h_int) cudaFreeHost(r.h_int);
+    if (r.h_flt) cudaFreeHost(r.h_flt);
+    cudaFree(r.d_int);
+    cudaFree(r.d_flt);
+    if (r.ev) cudaEventDestroy(r.ev);
+  }
+  cudaFree(t->d_stage);
+  cudaFree(t->d_out_poses);
+  cudaFree(t->d_stats);
+  cudaFree(t->d_trace);
+  cudaFree(t->d_trace_count);
+  if (t->h_out_poses) cudaFreeHost(t->h_out_poses);
+  if (t->h_stats) cudaFreeHost(t->h_stats);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uwt_default_config(uwt_config* cfg) {
+  if (!cfg) return UWT_E_INVALID;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->width = 640;
+  cfg->height = 480;
+  cfg->fx = 525.0f;  // calibration/calibrationTUM.xml:20
+  cfg->fy = 525.0f;
+  cfg->cx = 319.5f;
+  cfg->cy = 239.5f;
+  cfg->levels = 5;            // Options.cpp:26
+  cfg->first_level = 4;       // Tracker.cpp:368
+  cfg->last_level = 1;        // Tracker.cpp:369
+  cfg->max_iterations = 50;   // Tracker.cpp:366
+  cfg->epsilon = 0.001f;      // Tracker.cpp:364
+  cfg->residual_scale = 50.0f;      // Tracker.cpp:559
+  cfg->gradient_threshold = 20.0;   // Options.cpp:27
+  cfg->solve_mode = UWT_SOLVE_LU;
+  cfg->device = 0;
+  cfg->max_frames = 2;
+  cfg->cluster_size = 0;
+  cfg->flags = 0;
+  return UWT_OK;
+}
+
+int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
+  if (out) *out = nullptr;
+  if (!cfg || !out) return fail(nullptr, UWT_E_INVALID, "cfg/out is NULL");
+  const uwt_config& c = *cfg;
+  if (c.levels < 1 || c.levels > kMaxLevels)
+    return fail(nullptr, UWT_E_INVALID, "levels=%d unsupported (1..%d)", c.levels, kMaxLevels);
+  const int div = 1 << (c.levels - 1);
+  // The reference sizes levels as w>>l while cv::resize rounds: they only agree when the
+  // size is divisible by 2^(levels-1); 16-byte rows keep loads vectorised.
+  if (c.width <= 0 || c.height <= 0 || c.width % div || c.height % div || c.width % 16 ||
+      c.height % 2)
+    return fail(nullptr, UWT_E_INVALID,
+                "frame %dx%d must be divisible by 2^(levels-1)=%d and the width by 16", c.width,
+                c.height, div);
+  if ((c.width >> (c.levels - 1)) < 2 || (c.height >> (c.levels - 1)) < 2)
+    return fail(nullptr, UWT_E_INVALID, "coarsest level smaller than 2x2");
+  if (c.width > 4096 || c.height > 4096)
+    return fail(nullptr, UWT_E_INVALID, "frame larger than 4096 not supported (12-bit records)");
+  if (c.first_level >= c.levels || c.last_level < 0 || c.last_level > c.first_level)
+    return fail(nullptr, UWT_E_INVALID, "bad level range first=%d last=%d", c.first_level,
+                c.last_level);
+  if (c.max_iterations < 1 || c.max_frames < 1)
+    return fail(nullptr, UWT_E_INVALID, "max_iterations and max_frames must be >= 1");
+  if (c.solve_mode != UWT_SOLVE_LU && c.solve_mode != UWT_SOLVE_INVERSE)
+    return fail(nullptr, UWT_E_INVALID, "bad solve_mode %d", c.solve_mode);
+  if (c.cluster_size != 0 && c.cluster_size != 1 && c.cluster_size != 2 && c.cluster_size != 4 &&
+      c.cluster_size != 8 && c.cluster_size != 16)
+    return fail(nullptr, UWT_E_INVALID, "cluster_size must be 0, 1, 2, 4, 8 or 16");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, UWT_E_CUDA, "no CUDA device available (%s); there is no CPU fallback",
+                cudaGetErrorString(e));
+  if (c.device < 0 || c.device >= ndev)
+    return fail(nullptr, UWT_E_INVALID, "device %d out of range (0..%d)", c.device, ndev - 1);
+
+  uwt_tracker* t = new (std::nothrow) uwt_tracker();
+  if (!t) return fail(nullptr, UWT_E_NOMEM, "out of host memory");
+  t->cfg = c;
+  build_geom(c, t->geom);
+  t->slots.resize(c.max_frames);
+#define CREATE_CUDA(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      fail(nullptr, UWT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+      destroy_impl(t);                                                                 \
+      return UWT_E_CUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+  CREATE_CUDA(cudaSetDevice(c.device));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+  const Geom& g = t->geom;
+  const size_t F = (size_t)c.max_frames;
+  Pools& p = t->pools;
+  CREATE_CUDA(cudaMalloc(&p.img, F * g.plane_elems));
+  CREATE_CUDA(cudaMalloc(&p.gx, F * g.plane_elems * sizeof(int16_t)));
+  CREATE_CUDA(cudaMalloc(&p.gy, F * g.plane_elems * sizeof(int16_t)));
+  CREATE_CUDA(cudaMalloc(&p.g, F * g.plane_elems));
+  CREATE_CUDA(cudaMalloc(&p.gpart, F * g.tile_elems * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.ticket, F * kMaxLevels * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.ithr, F * kMaxLevels * sizeof(int)));
+  CREATE_CUDA(cudaMalloc(&p.cnt, F * g.cnt_elems * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.ncand, F * kMaxLevels * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.cand_xy, F * g.cand_elems * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.rec, F * g.rec_elems * sizeof(uint64_t)));
+  CREATE_CUDA(cudaMemsetAsync(p.ticket, 0, F * kMaxLevels * sizeof(uint32_t), t->stream));
+  CREATE_CUDA(cudaMemsetAsync(p.ncand, 0, F * kMaxLevels * sizeof(uint32_t), t->stream));
+  // pitch padding bytes are read (never used) by vector loads: keep them defined
+  CREATE_CUDA(cudaMemsetAsync(p.img, 0, F * g.plane_elems, t->stream));
+  CREATE_CUDA(cudaMemsetAsync(p.g, 0, F * g.plane_elems, t->stream));
+  for (ArgRegion& r : t->ring) {
+    CREATE_CUDA(cudaHostAlloc(&r.h_int, sizeof(int) * 2 * F, cudaHostAllocDefault));
+    CREATE_CUDA(cudaHostAlloc(&r.h_flt, sizeof(float) * 7 * F, cudaHostAllocDefault));
+    CREATE_CUDA(cudaMalloc(&r.d_int, sizeof(int) * 2 * F));
+    CREATE_CUDA(cudaMalloc(&r.d_flt, sizeof(float) * 7 * F));
+    CREATE_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+  }
+  const size_t frame_bytes = (size_t)c.width * c.height;
+  t->stage_frames = std::max<size_t>(1, std::min<size_t>(F, ((size_t)256 << 20) / frame_bytes));
+  CREATE_CUDA(cudaMalloc(&t->d_stage, t->stage_frames * frame_bytes));
+  CREATE_CUDA(cudaMalloc(&t->d_out_poses, sizeof(float) * 7 * F));
+  CREATE_CUDA(cudaMalloc(&t->d_stats, sizeof(uwt_track_stats) * F));
+  CREATE_CUDA(cudaHostAlloc(&t->h_out_poses, sizeof(float) * 7 * F, cudaHostAllocDefault));
+  CREATE_CUDA(cudaHostAlloc(&t->h_stats, sizeof(uwt_track_stats) * F, cudaHostAllocDefault));
+  if (c.flags & UWT_FLAG_TRACE) {
+    t->trace_cap = (c.first_level - c.last_level + 1) * c.max_iterations;
+    CREATE_CUDA(cudaMalloc(&t->d_trace, sizeof(uwt_iter_trace) * t->trace_cap * kTraceProblems));
+    CREATE_CUDA(cudaMalloc(&t->d_trace_count, sizeof(int) * kTraceProblems));
+  }
+  // largest cluster the device can co-schedule for the estimate kernel
+  t->max_cluster = 8;
+  {
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 9) {
+      fail(nullptr, UWT_E_CUDA, "device sm_%d%d has no thread-block clusters; built for sm_100a",
+           prop.major, prop.minor);
+      destroy_impl(t);
+      return UWT_E_CUDA;
+    }
+    if (prop.major >= 10) t->max_cluster = 16;
+  }
+  CREATE_CUDA(cudaStreamSynchronize(t->stream));
+#undef CREATE_CUDA
+  *out = t;
+  return UWT_OK;
+}
+
+int uwt_destroy(uwt_tracker* t) {
+  if (!t) return UWT_E_INVALID;
+  destroy_impl(t);
+  return UWT_OK;
+}
+
+const char* uwt_last_error(const uwt_tracker* t) {
+  return t ? t->error.c_str() : g_create_error.c_str();
+}
+
+int uwt_get_level_info(const uwt_tracker* t, int level, uwt_level_info* info) {
+  if (!t || !info || level < 0 || level >= t->geom.levels) return UWT_E_INVALID;
+  const LevelGeom& L = t->geom.lv[level];
+  info->width = L.w; info->height = L.h;
+  info->fx = L.fx; info->fy = L.fy; info->cx = L.cx; info->cy = L.cy;
+  info->invfx = L.invfx; info->invfy = L.invfy;
+  return UWT_OK;
+}
+
+void* uwt_stream(const uwt_tracker* t) { return t ? (void*)t->stream : nullptr; }
+
+int uwt_synchronize(uwt_tracker* t) {
+  if (!t) return UWT_E_INVALID;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  return UWT_OK;
+}
+
+long long uwt_launch_count(const uwt_tracker* t) { return t ? t->launches : 0; }
+
+static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t* dev_src,
+                          size_t row_stride, size_t frame_stride) {
+  ArgRegion* r;
+  int rc = acquire(t, &r);
+  if (rc) return rc;
+  rc = push_slots(t, r, n, slots, nullptr);
+  if (rc) return rc;
+  const int k = launch_pyramid(t->geom, t->pools, n, r->d_int, dev_src, row_stride, frame_stride,
+                               false, t->stream);
+  if (k < 0) return fail(t, UWT_E_CUDA, "pyramid kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  rc = release(t, r);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    SlotState& s = t->slots[slots[i]];
+    s.pyramid = true;
+    s.gradient = s.candidates = false;
+  }
+  return UWT_OK;
+}
+
+int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* host,
+                      size_t row_stride, size_t frame_stride) {
+  int rc = check_slots(t, n, slots);
+  if (rc) return rc;
+  if (!host || row_stride < (size_t)t->cfg.width)
+    return fail(t, UWT_E_INVALID, "host NULL or row_stride < width");
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  const size_t w = t->cfg.width, h = t->cfg.height;
+  for (size_t done = 0; done < (size_t)n;) {
+    const size_t cnt = std::min(t->stage_frames, (size_t)n - done);
+    const uint8_t* src = host + done * frame_stride;
+    if (frame_stride == row_stride * h) {
+      // frames are contiguous: one strided copy for the whole chunk
+      UWT_CUDA(t, cudaMemcpy2DAsync(t->d_stage, w, src, row_stride, w, h * cnt,
+                                    cudaMemcpyHostToDevice, t->stream));
+    } else {
+      for (size_t i = 0; i < cnt; ++i)
+        UWT_CUDA(t, cudaMemcpy2DAsync(t->d_stage + i * w * h, w, src + i * frame_stride,
+                                      row_stride, w, h, cudaMemcpyHostToDevice, t->stream));
+    }
+    rc = pyramid_common(t, (int)cnt, slots + done, t->d_stage, w, w * h);
+    if (rc) return rc;
+    done += cnt;
+  }
+  return UWT_OK;
+}
+
+int uwt_set_frames_device(uwt_tracker* t, int n, const int* slots, const uint8_t* dev,
+                          size_t row_stride, size_t frame_stride) {
+  int rc = check_slots(t, n, slots);
+  if (rc) return rc;
+  if (!dev || row_stride < (size_t)t->cfg.width)
+    return fail(t, UWT_E_INVALID, "dev NULL or row_stride < width");
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  return pyramid_common(t, n, slots, dev, row_stride, frame_stride);
+}
+
+int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {
+  int rc = check_slots(t, n, slots);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)
+    if (!t->slots[slots[i]].pyramid)
+      return fail(t, UWT_E_STATE, "slot %d has no frame", slots[i]);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  ArgRegion* r;
+  if ((rc = acquire(t, &r))) return rc;
+  if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
+  const int k = launch_gradient(t->geom, t->pools, n, r->d_int, t->stream);
+  if (k < 0) return fail(t, UWT_E_CUDA, "gradient kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  if ((rc = release(t, r))) return rc;
+  for (int i = 0; i < n; ++i) {
+    t->slots[slots[i]].gradient = true;
+    t->slots[slots[i]].candidates = false;
+  }
+  return UWT_OK;
+}
+
+int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
+  int rc = check_slots(t, n, slots);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)
+    if (!t->slots[slots[i]].gradient)
+      return fail(t, UWT_E_STATE, "slot %d has no gradients (call uwt_apply_gradient)", slots[i]);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  ArgRegion* r;
+  if ((rc = acquire(t, &r))) return rc;
+  if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
+  const int k = launch_candidates(t->geom, t->pools, n, r->d_int, t->stream);
+  if (k < 0) return fail(t, UWT_E_CUDA, "candidate kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  if ((rc = release(t, r))) return rc;
+  for (int i = 0; i < n; ++i) t->slots[slots[i]].candidates = true;
+  return UWT_OK;
+}
+
+static int pick_cluster(const uwt_tracker* t, int n) {
+  int c = t->cfg.cluster_size;
+  if (c == 0) {
+    // fill the 148 SMs: one CTA per problem for large batches, a 16-CTA cluster for one
+    c = 1;
+    while (c < 16 && n * c * 2 <= 148) c *= 2;
+  }
+  return std::min(c, t->max_cluster);
+}
+
+int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const int* cur_slots,
+                            const float* init_poses7) {
+  int rc = check_slots(t, n, prev_slots);
+  if (rc) return rc;
+  if ((rc = check_slots(t, n, cur_slots))) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (!t->slots[prev_slots[i]].candidates)
+      return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slots[i]);
+    if (!t->slots[cur_slots[i]].pyramid)
+      return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slots[i]);
+  }
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  ArgRegion* r;
+  if ((rc = acquire(t, &r))) return rc;
+  if ((rc = push_slots(t, r, n, prev_slots, cur_slots))) return rc;
+  if (init_poses7) {
+    std::memcpy(r->h_flt, init_poses7, sizeof(float) * 7 * n);
+    UWT_CUDA(t, cudaMemcpyAsync(r->d_flt, r->h_flt, sizeof(float) * 7 * n,
+                                cudaMemcpyHostToDevice, t->stream));
+  }
+  EstimateIO io;
+  io.prev_slots = r->d_int;
+  io.cur_slots = r->d_int + n;
+  io.init_poses = init_poses7 ? r->d_flt : nullptr;
+  io.out_poses = t->d_out_poses;
+  io.stats = t->d_stats;
+  const bool tracing = t->d_trace && n <= kTraceProblems;
+  io.trace = tracing ? t->d_trace : nullptr;
+  io.trace_count = tracing ? t->d_trace_count : nullptr;
+  io.trace_cap = t->trace_cap;
+  int cluster = pick_cluster(t, n);
+  int k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream);
+  while (k < 0 && cluster > 1) {  // a 16-CTA cluster may not be schedulable on every part
+    cudaGetLastError();
+    cluster /= 2;
+    t->max_cluster = cluster;
+    k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream);
+  }
+  if (k < 0) return fail(t, UWT_E_CUDA, "estimate kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  UWT_CUDA(t, cudaMemcpyAsync(t->h_out_poses, t->d_out_poses, sizeof(float) * 7 * n,
+                              cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, t->d_stats, sizeof(uwt_track_stats) * n,
+                              cudaMemcpyDeviceToHost, t->stream));
+  if ((rc = release(t, r))) return rc;
+  t->last_n = n;
+  return UWT_OK;
+}
+
+int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* stats) {
+  if (!t) return UWT_E_INVALID;
+  if (n <= 0 || n > t->last_n) return fail(t, UWT_E_INVALID, "n=%d exceeds the last batch (%d)", n, t->last_n);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  if (out_poses7) std::memcpy(out_poses7, t->h_out_poses, sizeof(float) * 7 * n);
+  if (stats) std::memcpy(stats, t->h_stats, sizeof(uwt_track_stats) * n);
+  return UWT_OK;
+}
+
+int uwt_estimate_pose(uwt_tracker* t, int n, const int* prev_slots, const int* cur_slots,
+                      const float* init_poses7, float* out_poses7, uwt_track_stats* stats) {
+  int rc = uwt_estimate_pose_async(t, n, prev_slots, cur_slots, init_poses7);
+  if (rc) return rc;
+  return uwt_fetch_poses(t, n, out_poses7, stats);
+}
+
+int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,
+                    float* out4) {
+  if (!t) return UWT_E_INVALID;
+  if (!pts4 || !pose7 || !out4 || n < 0 || level < 0 || level >= t->geom.levels)
+    return fail(t, UWT_E_INVALID, "bad argument to uwt_warp_points");
+  if (n == 0) return UWT_OK;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  float *d_pts = nullptr, *d_out = nullptr, *d_pose = nullptr;
+  UWT_CUDA(t, cudaMalloc(&d_pts, sizeof(float) * 4 * n));
+  UWT_CUDA(t, cudaMalloc(&d_out, sizeof(float) * 4 * n));
+  UWT_CUDA(t, cudaMalloc(&d_pose, sizeof(float) * 7));
+  cudaMemcpyAsync(d_pts, pts4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, t->stream);
+  cudaMemcpyAsync(d_pose, pose7, sizeof(float) * 7, cudaMemcpyHostToDevice, t->stream);
+  const int k = launch_warp_points(t->geom, d_pts, n, d_pose, level, d_out, t->stream);
+  if (k > 0) t->launches += k;
+  cudaMemcpyAsync(out4, d_out, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, t->stream);
+  cudaError_t e = cudaStreamSynchronize(t->stream);
+  cudaFree(d_pts);
+  cudaFree(d_out);
+  cudaFree(d_pose);
+  if (k < 0 || e != cudaSuccess)
+    return fail(t, UWT_E_CUDA, "warp kernel failed: %s", cudaGetErrorString(e));
+  return UWT_OK;
+}
+
+static int check_read(uwt_tracker* t, int slot, int level) {
+  if (!t) return UWT_E_INVALID;
+  if (slot < 0 || slot >= t->cfg.max_frames || level < 0 || level >= t->geom.levels)
+    return fail(t, UWT_E_INVALID, "slot %d / level %d out of range", slot, level);
+  return UWT_OK;
+}
+
+int uwt_get_image(uwt_tracker* t, int slot, int level, uint8_t* host) {
+  int rc = check_read(t, slot, level);
+  if (rc) return rc;
+  if (!t->slots[slot].pyramid) return fail(t, UWT_E_STATE, "slot %d has no frame", slot);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  const LevelGeom& L = t->geom.lv[level];
+  const size_t off = (size_t)slot * t->geom.plane_elems + L.plane_off;
+  UWT_CUDA(t, cudaMemcpy2DAsync(host, L.w, t->pools.img + off, L.pitch, L.w, L.h,
+                                cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  return UWT_OK;
+}
+
+int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t* gy, uint8_t* g) {
+  int rc = check_read(t, slot, level);
+  if (rc) return rc;
+  if (!t->slots[slot].gradient) return fail(t, UWT_E_STATE, "slot %d has no gradients", slot);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  const LevelGeom& L = t->geom.lv[level];
+  const size_t off = (size_t)slot * t->geom.plane_elems + L.plane_off;
+  if (gx)
+    UWT_CUDA(t, cudaMemcpy2DAsync(gx, L.w * 2, t->pools.gx + off, L.pitch * 2, L.w * 2, L.h,
+                                  cudaMemcpyDeviceToHost, t->stream));
+  if (gy)
+    UWT_CUDA(t, cudaMemcpy2DAsync(gy, L.w * 2, t->pools.gy + off, L.pitch * 2, L.w * 2, L.h,
+                                  cudaMemcpyDeviceToHost, t->stream));
+  if (g)
+    UWT_CUDA(t, cudaMemcpy2DAsync(g, L.w, t->pools.g + off, L.pitch, L.w, L.h,
+                                  cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  return UWT_OK;
+}
+
+int uwt_get_candidate_count(uwt_tracker* t, int slot, int level, int* n) {
+  int rc = check_read(t, slot, level);
+  if (rc) return rc;
+  if (!n) return fail(t, UWT_E_INVALID, "n is NULL");
+  if (!t->slots[slot].candidates) return fail(t, UWT_E_STATE, "slot %d has no candidates", slot);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  uint32_t v = 0;
+  UWT_CUDA(t, cudaMemcpyAsync(&v, t->pools.ncand + (size_t)slot * kMaxLevels + level, sizeof(v),
+                              cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  *n = (int)v;
+  return UWT_OK;
+}
+
+int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int capacity_rows,
+                       int* n) {
+  int cnt = 0;
+  int rc = uwt_get_candidate_count(t, slot, level, &cnt);
+  if (rc) return rc;
+  if (n) *n = cnt;
+  if (!pts4) return UWT_OK;
+  if (cnt > capacity_rows)
+    return fail(t, UWT_E_INVALID, "capacity %d < %d candidates", capacity_rows, cnt);
+  if (cnt == 0) return UWT_OK;
+  std::vector<uint32_t> xy(cnt);
+  const LevelGeom& L = t->geom.lv[level];
+  UWT_CUDA(t, cudaMemcpyAsync(xy.data(),
+                              t->pools.cand_xy + (size_t)slot * t->geom.cand_elems + L.cand_off,
+                              sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  for (int i = 0; i < cnt; ++i) {  // candidatePoints_ rows, Tracker.cpp:1351-1355
+    pts4[i * 4 + 0] = (float)(xy[i] & 0xFFFFu);
+    pts4[i * 4 + 1] = (float)(xy[i] >> 16);
+    pts4[i * 4 + 2] = 1.0f;
+    pts4[i * 4 + 3] = 1.0f;
+  }
+  return UWT_OK;
+}
+
+int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, int* n) {
+  if (!t) return UWT_E_INVALID;
+  if (!t->d_trace) return fail(t, UWT_E_STATE, "tracker was not created with UWT_FLAG_TRACE");
+  if (index < 0 || index >= t->last_n || index >= kTraceProblems || !out || !n)
+    return fail(t, UWT_E_INVALID, "bad trace index %d", index);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  int cnt = 0;
+  UWT_CUDA(t, cudaMemcpyAsync(&cnt, t->d_trace_count + index, sizeof(int), cudaMemcpyDeviceToHost,
+                              t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  cnt = std::min(cnt, capacity);
+  if (cnt > 0) {
+    UWT_CUDA(t, cudaMemcpyAsync(out, t->d_trace + (size_t)index * t->trace_cap,
+                                sizeof(uwt_iter_trace) * cnt, cudaMemcpyDeviceToHost, t->stream));
+    UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  }
+  *n = cnt;
+  return UWT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+// uwt_image_kernels.cu -- K1 (pyramid) and K2 (Scharr gradients + gradient image).
+//
+// K1 restates the pyramid loop of System::AddFrame (/root/reference/src/System.cpp:246-251):
+//     cv::resize(img[l-1], img[l], Size(), 0.5, 0.5)  ==  (a + b + c + d + 2) >> 2
+// for ALL levels in one pass over level 0 (one 64x64 tile per CTA, reduced in shared memory).
+//
+// K2 restates Tracker::ApplyGradient (src/Tracker.cpp:1127-1143) for all levels in one
+// launch: Scharr x / y as int16 with BORDER_REFLECT_101, min(|.|,255) and the 0.5/0.5 blend
+// with ties-to-even.  Tiles are staged in shared memory with their halo by the bulk-copy
+// engine (cp.async.bulk + mbarrier), one bulk copy per tile row.  The per-level sum of the
+// gradient image (needed for the candidate threshold, Tracker.cpp:1325-1327) is reduced in
+// the same kernel; the last CTA of a level turns it into the integer threshold.
+#include "uwt_internal.cuh"
+
+namespace uwt {
+
+// ----------------------------------------------------------------------------------------
+// K1: pyramid
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pyramid_kernel(const __grid_constant__ Geom geom, const Pools pools, const int* __restrict__ slots,
+               const uint8_t* __restrict__ src, size_t row_stride, size_t frame_stride,
+               int src_is_slot, int src_aligned) {
+  __shared__ __align__(16) uint8_t s0[kPyrTile][kPyrTile];
+  __shared__ __align__(16) uint8_t s1[32][32];
+  __shared__ uint8_t s2[16][16];
+  __shared__ uint8_t s3[8][8];
+  __shared__ uint8_t s4[4][4];
+  __shared__ uint8_t s5[2][2];
+
+  const int t = threadIdx.x;
+  const int slot = slots[blockIdx.z];
+  const int x0 = blockIdx.x * kPyrTile, y0 = blockIdx.y * kPyrTile;
+  const LevelGeom& L0 = geom.lv[0];
+  uint8_t* plane = pools.img + (size_t)slot * geom.plane_elems;
+
+  // ---- level 0 tile: 256 threads x 16 bytes ----
+  {
+    const int r = t >> 2, c = (t & 3) * 16;
+    const int gx = x0 + c, gy = y0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gx < L0.w && gy < L0.h) {  // w is a multiple of 16: a 16-byte group is all in or out
+      const uint8_t* sp =
+          src_is_slot ? plane + L0.plane_off + (size_t)gy * L0.pitch + gx
+                      : src + (size_t)blockIdx.z * frame_stride + (size_t)gy * row_stride + gx;
+      if (src_aligned) {
+        v = *reinterpret_cast<const uint4*>(sp);
+      } else {
+        uint32_t w4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w4[i] = sp[4 * i] | (sp[4 * i + 1] << 8) | (sp[4 * i + 2] << 16) | (sp[4 * i + 3] << 24);
+        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      if (!src_is_slot)
+        *reinterpret_cast<uint4*>(plane + L0.plane_off + (size_t)gy * L0.pitch + gx) = v;
+    }
+    *reinterpret_cast<uint4*>(&s0[r][c]) = v;
+  }
+  __syncthreads();
+
+  // ---- level 1: 32 x 32, four outputs per thread ----
+  if (geom.levels > 1) {
+    const LevelGeom& L = geom.lv[1];
+    const int r = t >> 3, c = (t & 7) * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(&s0[2 * r][2 * c]);
+    const uint2 b = *reinterpret_cast<const uint2*>(&s0[2 * r + 1][2 * c]);
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t aw = (i < 2) ? a.x : a.y, bw = (i < 2) ? b.x : b.y;
+      const int sh = (i & 1) * 16;
+      const uint32_t s = ((aw >> sh) & 0xFF) + ((aw >> (sh + 8)) & 0xFF) + ((bw >> sh) & 0xFF) +
+                         ((bw >> (sh + 8)) & 0xFF) + 2;
+      out |= (s >> 2) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(&s1[r][c]) = out;
+    const int gx = (x0 >> 1) + c, gy = (y0 >> 1) + r;
+    if (gx < L.w && gy < L.h)  // w1 is a multiple of 8
+      *reinterpret_cast<uint32_t*>(plane + L.plane_off + (size_t)gy * L.pitch + gx) = out;
+  }
+  __syncthreads();
+
+  // ---- levels 2..6: one output per thread ----
+#define UWT_DOWN(LVL, SRC, DST, DIM)                                                         \
+  if (geom.levels > LVL) {                                                                   \
+    if (t < DIM * DIM) {                                                                     \
+      const LevelGeom& L = geom.lv[LVL];                                                     \
+      const int r = t / DIM, c = t % DIM;                                                    \
+      const uint32_t s = SRC[2 * r][2 * c] + SRC[2 * r][2 * c + 1] + SRC[2 * r + 1][2 * c] + \
+                         SRC[2 * r + 1][2 * c + 1] + 2;                                      \
+      const uint8_t o = (uint8_t)(s >> 2);                                                   \
+      DST[r][c] = o;                                                                         \
+      const int gx = (x0 >> LVL) + c, gy = (y0 >> LVL) + r;                                  \
+      if (gx < L.w && gy < L.h) plane[L.plane_off + (size_t)gy * L.pitch + gx] = o;          \
+    }                                                                                        \
+    __syncthreads();                                                                         \
+  }
+  UWT_DOWN(2, s1, s2, 16)
+  UWT_DOWN(3, s2, s3, 8)
+  UWT_DOWN(4, s3, s4, 4)
+  UWT_DOWN(5, s4, s5, 2)
+#undef UWT_DOWN
+  if (geom.levels > 6 && t == 0) {
+    const LevelGeom& L = geom.lv[6];
+    const uint32_t s = s5[0][0] + s5[0][1] + s5[1][0] + s5[1][1] + 2;
+    const int gx = x0 >> 6, gy = y0 >> 6;
+    if (gx < L.w && gy < L.h) plane[L.plane_off + (size_t)gy * L.pitch + gx] = (uint8_t)(s >> 2);
+  }
+}
+
+int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
+                   size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st) {
+  const LevelGeom& L0 = g.lv[0];
+  dim3 grid((L0.w + kPyrTile - 1) / kPyrTile, (L0.h + kPyrTile - 1) / kPyrTile, n);
+  const int aligned =
+      src_is_slot || ((((uintptr_t)src) | row_stride | frame_stride) & 15) == 0 ? 1 : 0;
+  pyramid_kernel<<<grid, 256, 0, st>>>(g, p, d_slots, src, row_stride, frame_stride,
+                                       src_is_slot ? 1 : 0, aligned);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ----------------------------------------------------------------------------------------
+// K2: gradients
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+constexpr int kHaloX = 16;                               // 16-byte aligned halo
+constexpr int kTileRowBytes = kGradTileW + 2 * kHaloX;   // 160
+constexpr int kTileRows = kGradTileH + 2;                // 34
+
+struct RowVals {
+  int hx[4];  // v[i+1] - v[i-1]
+  int sm[4];  // 3 v[i-1] + 10 v[i] + 3 v[i+1]
+};
+
+__device__ __forceinline__ RowVals row_vals(const uint8_t* srow, int sx, bool left_edge,
+                                            bool right_edge, int nvalid) {
+  // srow: tile row in shared memory; sx: byte index of the 4-pixel group (multiple of 4)
+  const uint32_t c = *reinterpret_cast<const uint32_t*>(srow + sx);
+  int v[6];
+  v[1] = c & 0xFF;
+  v[2] = (c >> 8) & 0xFF;
+  v[3] = (c >> 16) & 0xFF;
+  v[4] = c >> 24;
+  v[0] = left_edge ? v[2] : srow[sx - 1];  // REFLECT_101: x = -1 -> 1
+  v[5] = srow[sx + 4];
+  if (right_edge) {
+    // the image ends inside this group after nvalid pixels: x = w -> w - 2
+    if (nvalid == 4) v[5] = v[3];
+    else if (nvalid == 3) v[4] = v[2];
+    else if (nvalid == 2) v[3] = v[1];
+    else v[2] = v[0];
+  }
+  RowVals r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.hx[i] = v[i + 2] - v[i];
+    r.sm[i] = 3 * v[i] + 10 * v[i + 1] + 3 * v[i + 2];
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
+                const int* __restrict__ slots) {
+  __shared__ __align__(128) uint8_t tile[kTileRows][kTileRowBytes];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t warp_sums[8];
+  __shared__ int is_last;
+
+  const int t = threadIdx.x;
+  const int slot = slots[blockIdx.y];
+  // locate (level, tile) from the flattened tile index
+  int lvl = 0, tidx = blockIdx.x;
+  while (lvl + 1 < geom.levels && tidx >= geom.lv[lvl + 1].tile_off) ++lvl;
+  // tile_off is cumulative and increasing with the level; find the last level whose
+  // tile_off <= tidx
+  tidx -= geom.lv[lvl].tile_off;
+  const LevelGeom& L = geom.lv[lvl];
+  const int tx = tidx % L.tiles_x, ty = tidx / L.tiles_x;
+  const int x0 = tx * kGradTileW, y0 = ty * kGradTileH;
+  const size_t plane_base = (size_t)slot * geom.plane_elems + L.plane_off;
+  const uint8_t* img = pools.img + plane_base;
+
+  // ---- stage the tile + halo: rows [y0-1, y0+H], bytes [x0-16, x0+W+16) clipped ----
+  const int row_lo = max(y0 - 1, 0), row_hi = min(y0 + kGradTileH, L.h - 1);  // inclusive
+  const int col_lo = max(x0 - kHaloX, 0), col_hi = min(x0 + kGradTileW + kHaloX, L.pitch);
+  const uint32_t row_bytes = (uint32_t)(col_hi - col_lo);
+  if (t == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)(row_hi - row_lo + 1));
+  if (t < kTileRows) {
+    const int gy = y0 - 1 + t;
+    if (gy >= row_lo && gy <= row_hi)
+      bulk_g2s(&tile[t][col_lo - (x0 - kHaloX)], img + (size_t)gy * L.pitch + col_lo, row_bytes,
+               &bar);
+  }
+  mbar_wait(&bar, 0);
+
+  // ---- compute: warp = 4 rows, lane = 4 pixels ----
+  const int lane = t & 31, wy = t >> 5;
+  const int xg = x0 + lane * 4;
+  const int sx = kHaloX + lane * 4;
+  uint32_t gsum = 0;
+  if (xg < L.w) {
+    const int nvalid = min(4, L.w - xg);
+    const bool left_edge = (xg == 0);
+    const bool right_edge = (xg + 4 >= L.w);
+    const int ybase = y0 + wy * 4;
+    auto srow = [&](int y) -> const uint8_t* {
+      // REFLECT_101 on rows: -1 -> 1, h -> h - 2
+      const int yy = y < 0 ? -y : (y >= L.h ? 2 * L.h - 2 - y : y);
+      return tile[yy - (y0 - 1)];
+    };
+    if (ybase < L.h) {
+      RowVals rm = row_vals(srow(ybase - 1), sx, left_edge, right_edge, nvalid);
+      RowVals r0 = row_vals(srow(ybase), sx, left_edge, right_edge, nvalid);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = ybase + j;
+        if (y >= L.h) break;
+        RowVals rp = row_vals(srow(y + 1), sx, left_edge, right_edge, nvalid);
+        int vx[4], vy[4];
+        uint32_t gq = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vx[i] = 3 * rm.hx[i] + 10 * r0.hx[i] + 3 * rp.hx[i];
+          vy[i] = rp.sm[i] - rm.sm[i];
+          const int ax = min(abs(vx[i]), 255), ay = min(abs(vy[i]), 255);
+          const int s = ax + ay;
+          const uint32_t gv = (uint32_t)((s + ((s >> 1) & 1)) >> 1);  // ties to even
+          if (i < nvalid) gsum += gv;
+          gq |= gv << (8 * i);
+        }
+        const size_t o = plane_base + (size_t)y * L.pitch + xg;
+        if (nvalid == 4) {
+          *reinterpret_cast<uint2*>(pools.gx + o) =
+              make_uint2((vx[0] & 0xFFFF) | (vx[1] << 16), (vx[2] & 0xFFFF) | (vx[3] << 16));
+          *reinterpret_cast<uint2*>(pools.gy + o) =
+              make_uint2((vy[0] & 0xFFFF) | (vy[1] << 16), (vy[2] & 0xFFFF) | (vy[3] << 16));
+          *reinterpret_cast<uint32_t*>(pools.g + o) = gq;
+        } else {
+          for (int i = 0; i < nvalid; ++i) {
+            pools.gx[o + i] = (int16_t)vx[i];
+            pools.gy[o + i] = (int16_t)vy[i];
+            pools.g[o + i] = (uint8_t)(gq >> (8 * i));
+          }
+        }
+        rm = r0;
+        r0 = rp;
+      }
+    }
+  }
+
+  // ---- per-tile sum of g, then the last CTA of the level makes the threshold ----
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+  if (lane == 0) warp_sums[wy] = gsum;
+  __syncthreads();
+  const int ntiles = L.tiles_x * L.tiles_y;
+  uint32_t* gpart = pools.gpart + (size_t)slot * geom.tile_elems + L.tile_off;
+  if (t == 0) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += warp_sums[i];
+    gpart[tidx] = s;
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&pools.ticket[(size_t)slot * kMaxLevels + lvl], 1u);
+    is_last = (ticket == (uint32_t)ntiles - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    // fixed-order (deterministic) sum of the per-tile partials; integers, so exact
+    unsigned long long s = 0;
+    for (int i = t; i < ntiles; i += 256) s += __ldcg(&gpart[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long wsum[8];
+    if (lane == 0) wsum[wy] = s;
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long S = 0;
+      for (int i = 0; i < 8; ++i) S += wsum[i];
+      // Tracker.cpp:1325-1329: thres = mean + GRADIENT_THRESHOLD (float); 8-bit threshold
+      // compares against floor(thres)  (ARITHMETIC.md U6)
+      const double mean = (double)S / (double)((long long)L.w * L.h);
+      const float thres = (float)(mean + geom.gradient_threshold);
+      pools.ithr[(size_t)slot * kMaxLevels + lvl] = (int)floorf(thres);
+      pools.ticket[(size_t)slot * kMaxLevels + lvl] = 0;  // re-arm for the next frame
+    }
+  }
+}
+
+int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st) {
+  dim3 grid(g.grad_tiles_total, n);
+  gradient_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace uwt

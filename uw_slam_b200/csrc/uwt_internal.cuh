@@ -1,0 +1,90 @@
+// uwt_internal.cuh -- shared declarations of libuwtrack (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/uwtrack.h"
+
+namespace uwt {
+
+constexpr int kMaxLevels = UWT_MAX_LEVELS;
+
+// Gradient tile (K2): 128 x 32 pixels, staged with a 16-byte-aligned halo by cp.async.bulk.
+constexpr int kGradTileW = 128;
+constexpr int kGradTileH = 32;
+// Candidate compaction (K3): one warp owns a 128-column strip x kSegRows rows.
+constexpr int kStripW = 128;
+constexpr int kSegRows = 32;
+// Pyramid tile (K1): 64 x 64 level-0 pixels -> 32x32, 16x16, 8x8, 4x4, 2x2, 1x1.
+constexpr int kPyrTile = 64;
+
+// Packed candidate record consumed by the Gauss-Newton kernel (8 bytes / point):
+//   bits  0..11 x, 12..23 y, 24..31 I1, 32..44 gx (13-bit two's complement), 45..57 gy.
+// |gx|,|gy| <= 16*255 = 4080 < 4096 (Scharr weights sum to 16).
+__host__ __device__ inline uint64_t pack_record(uint32_t x, uint32_t y, uint32_t i1, int gx,
+                                                int gy) {
+  return (uint64_t)(x & 0xFFFu) | ((uint64_t)(y & 0xFFFu) << 12) | ((uint64_t)(i1 & 0xFFu) << 24) |
+         ((uint64_t)((uint32_t)gx & 0x1FFFu) << 32) | ((uint64_t)((uint32_t)gy & 0x1FFFu) << 45);
+}
+
+struct LevelGeom {
+  int w, h, pitch;     // pitch in elements, multiple of 16
+  int plane_off;       // element offset of this level inside a slot's image/gradient planes
+  int cand_off;        // element offset inside a slot's candidate (x,y) list
+  int rec_off;         // element offset inside a slot's record list, -1 if not optimised
+  int nstrip, nseg;    // compaction decomposition
+  int cnt_off;         // offset inside a slot's per-(column,segment) count array
+  int tiles_x, tiles_y;
+  int tile_off;        // offset inside a slot's per-tile gradient partial sums
+  float fx, fy, cx, cy, invfx, invfy;
+};
+
+struct Geom {
+  LevelGeom lv[kMaxLevels];
+  int levels, first_level, last_level, max_iterations;
+  float epsilon, residual_scale;
+  double gradient_threshold;
+  int solve_mode;
+  // per-slot strides (elements)
+  size_t plane_elems, cand_elems, rec_elems, cnt_elems, tile_elems;
+  int grad_tiles_total;  // gradient tiles per slot over all levels
+  int warp_items_total;  // compaction warp-items per slot over all levels
+};
+
+// Device memory pools, indexed [slot].
+struct Pools {
+  uint8_t* img;         // [slot][plane_elems]
+  int16_t* gx;          // [slot][plane_elems]
+  int16_t* gy;          // [slot][plane_elems]
+  uint8_t* g;           // [slot][plane_elems]
+  uint32_t* gpart;      // [slot][tile_elems]   per-tile sums of g
+  uint32_t* ticket;     // [slot][levels]       last-block tickets (self-resetting)
+  int* ithr;            // [slot][kMaxLevels]   integer threshold per level
+  uint32_t* cnt;        // [slot][cnt_elems]    counts, then exclusive offsets
+  uint32_t* ncand;      // [slot][kMaxLevels]
+  uint32_t* cand_xy;    // [slot][cand_elems]   x | y << 16, reference (x-major) order
+  uint64_t* rec;        // [slot][rec_elems]    packed records, same order
+};
+
+struct EstimateIO {
+  const int* prev_slots;
+  const int* cur_slots;
+  const float* init_poses;  // nullable, [n][7]
+  float* out_poses;         // [n][7]
+  uwt_track_stats* stats;   // [n]
+  uwt_iter_trace* trace;    // nullable, [n][trace_cap]
+  int* trace_count;         // [n]
+  int trace_cap;
+};
+
+// kernel launchers (each returns the number of kernels launched, or <0 on launch error)
+int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
+                   size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st);
+int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
+int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
+int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
+                    cudaStream_t st);
+int launch_warp_points(const Geom& g, const float* d_pts4, int n, const float* d_pose7, int level,
+                       float* d_out4, cudaStream_t st);
+
+}  // namespace uwt

@@ -1,0 +1,281 @@
+"""Host-side mirror of the reference's Tracker / CameraModel / Frame surface, on top of the
+C ABI (include/uwtrack.h).  Method names follow /root/reference/include/Tracker.h:
+InitializePyramid, ApplyGradient, ObtainCandidatePoints, EstimatePose, WarpFunction.
+
+The C++ facade (include/uw/uw_tracker.hpp) is what a C++ `System` links against; this file
+is the same surface for Python callers (tests, bench).
+"""
+import ctypes as C
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from . import _lib as L
+
+
+class UwtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("uwtrack error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CameraModel:
+    """uw::CameraModel (include/CameraModel.h:42-145) for rectified pinhole input.
+
+    Reads the reference's calibration XML (calibration/*.xml): in/out size, fx fy cx cy and
+    the four distortion coefficients; normalised intrinsics (cx, cy < 1) are rescaled by the
+    input size as in src/CameraModel.cpp:61-68.  Undistortion maps are out of scope: a
+    non-zero first distortion coefficient is reported by IsValid() but not applied.
+    """
+
+    def __init__(self):
+        self.in_width = self.in_height = self.out_width = self.out_height = 0
+        self.calib = np.zeros(4, np.float32)
+        self.dist = np.zeros(4, np.float32)
+        self.valid = False
+
+    def GetCameraModel(self, path):
+        root = ET.parse(path).getroot()
+
+        def num(tag):
+            return int(root.find(tag).text.split()[0])
+
+        def mat(tag):
+            return np.array(root.find(tag).find("data").text.split(), np.float32)
+
+        self.in_width, self.in_height = num("in_width"), num("in_height")
+        self.out_width, self.out_height = num("out_width"), num("out_height")
+        self.calib = mat("calibration_values")
+        self.dist = mat("rectification")
+        if self.calib[2] < 1 and self.calib[3] < 1:  # CameraModel.cpp:61-68
+            self.calib = self.calib * np.array([self.in_width, self.in_height,
+                                                self.in_width, self.in_height], np.float32)
+        self.valid = bool(self.dist[0] != 0)  # CameraModel.cpp:78-83
+        return self
+
+    @classmethod
+    def from_intrinsics(cls, width, height, fx, fy, cx, cy):
+        m = cls()
+        m.in_width = m.out_width = width
+        m.in_height = m.out_height = height
+        m.calib = np.array([fx, fy, cx, cy], np.float32)
+        return m
+
+    def GetK(self):
+        K = np.zeros((3, 3), np.float32)
+        K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = (self.calib[0], self.calib[1],
+                                                       self.calib[2], self.calib[3], 1)
+        return K
+
+    def GetOutputWidth(self):
+        return self.out_width
+
+    def GetOutputHeight(self):
+        return self.out_height
+
+    def GetInputWidth(self):
+        return self.in_width
+
+    def GetInputHeight(self):
+        return self.in_height
+
+    def IsValid(self):
+        return self.valid
+
+
+class Frame:
+    """uw::Frame (include/System.h:63-103): a handle on one device-side frame slot."""
+
+    def __init__(self, tracker, slot):
+        self._t = tracker
+        self.slot = slot
+        self.obtained_gradients_ = False
+        self.obtained_candidatePoints_ = False
+        self.rigid_transformation_ = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+
+    def image(self, lvl):
+        return self._t.get_image(self.slot, lvl)
+
+    def gradients(self, lvl):
+        return self._t.get_gradients(self.slot, lvl)
+
+    def candidatePoints(self, lvl):
+        return self._t.get_candidates(self.slot, lvl)
+
+
+class Tracker:
+    """uw::Tracker (include/Tracker.h:90-531), direct photometric path only."""
+
+    def __init__(self, depth_available=False, **cfg):
+        if depth_available:
+            raise UwtError(L.E_INVALID, "depth input is out of scope (SURVEY.md 8-f)")
+        self._lib = L.load()
+        self._h = None
+        self._cfg_overrides = cfg
+        self.cfg = None
+        self._keep = []
+
+    # -- Tracker::InitializePyramid(int w, int h, Mat K), Tracker.cpp:297 -------------------
+    def InitializePyramid(self, width, height, K, **cfg):
+        c = L.Config()
+        self._lib.uwt_default_config(C.byref(c))
+        c.width, c.height = width, height
+        c.fx, c.fy, c.cx, c.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+        for k, v in {**self._cfg_overrides, **cfg}.items():
+            if not hasattr(c, k):
+                raise AttributeError(k)
+            setattr(c, k, v)
+        h = L._H()
+        rc = self._lib.uwt_create(C.byref(c), C.byref(h))
+        if rc != 0:
+            raise UwtError(rc, self._lib.uwt_last_error(None).decode())
+        self._h, self.cfg = h, c
+        return self
+
+    def close(self):
+        if self._h is not None:
+            self._lib.uwt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise UwtError(rc, self._lib.uwt_last_error(self._h).decode())
+
+    @staticmethod
+    def _slots(s):
+        a = np.ascontiguousarray(np.atleast_1d(s), np.int32)
+        return a, a.ctypes.data_as(L._ip), int(a.size)
+
+    def level_info(self, lvl):
+        info = L.LevelInfo()
+        self._check(self._lib.uwt_get_level_info(self._h, lvl, C.byref(info)))
+        return info
+
+    # -- System::AddFrame pyramid loop, System.cpp:246-251 ----------------------------------
+    def AddFrames(self, slots, frames):
+        """frames: u8 array [n, H, W] (or [H, W]) in host memory."""
+        a, p, n = self._slots(slots)
+        f = np.ascontiguousarray(frames, np.uint8).reshape(n, self.cfg.height, self.cfg.width)
+        self._check(self._lib.uwt_upload_frames(self._h, n, p, f.ctypes.data, self.cfg.width,
+                                                self.cfg.width * self.cfg.height))
+        return [Frame(self, int(s)) for s in a]
+
+    def AddFramesHostPtr(self, slots, ptr, row_stride, frame_stride):
+        a, p, n = self._slots(slots)
+        self._check(self._lib.uwt_upload_frames(self._h, n, p, ptr, row_stride, frame_stride))
+
+    def AddFramesDevice(self, slots, dev_ptr, row_stride=None, frame_stride=None):
+        a, p, n = self._slots(slots)
+        rs = row_stride or self.cfg.width
+        fs = frame_stride or rs * self.cfg.height
+        self._check(self._lib.uwt_set_frames_device(self._h, n, p, dev_ptr, rs, fs))
+
+    # -- Tracker::ApplyGradient(Frame*), Tracker.cpp:1127 ------------------------------------
+    def ApplyGradient(self, frames):
+        a, p, n = self._slots(self._as_slots(frames))
+        self._check(self._lib.uwt_apply_gradient(self._h, n, p))
+        for f in self._as_frames(frames):
+            f.obtained_gradients_ = True
+
+    # -- Tracker::ObtainCandidatePoints(Frame*), Tracker.cpp:1314 ----------------------------
+    def ObtainCandidatePoints(self, frames):
+        a, p, n = self._slots(self._as_slots(frames))
+        self._check(self._lib.uwt_select_candidates(self._h, n, p))
+        for f in self._as_frames(frames):
+            f.obtained_candidatePoints_ = True
+
+    # -- Tracker::EstimatePose(Frame* prev, Frame* cur), Tracker.cpp:362 ---------------------
+    def EstimatePose(self, prev, cur, init_poses=None, return_stats=False):
+        pa, pp, n = self._slots(self._as_slots(prev))
+        ca, cp, n2 = self._slots(self._as_slots(cur))
+        assert n == n2
+        out = np.empty((n, 7), np.float32)
+        stats = (L.TrackStats * n)()
+        ip = None
+        if init_poses is not None:
+            ipa = np.ascontiguousarray(init_poses, np.float32).reshape(n, 7)
+            ip = ipa.ctypes.data_as(L._fp)
+        self._check(self._lib.uwt_estimate_pose(self._h, n, pp, cp, ip,
+                                                out.ctypes.data_as(L._fp), stats))
+        for f, pose in zip(self._as_frames(prev), out):
+            f.rigid_transformation_ = pose.copy()  # Tracker.cpp:595
+        return (out, list(stats)) if return_stats else out
+
+    def EstimatePoseAsync(self, prev, cur):
+        pa, pp, n = self._slots(self._as_slots(prev))
+        ca, cp, _ = self._slots(self._as_slots(cur))
+        self._check(self._lib.uwt_estimate_pose_async(self._h, n, pp, cp, None))
+
+    def FetchPoses(self, n):
+        out = np.empty((n, 7), np.float32)
+        self._check(self._lib.uwt_fetch_poses(self._h, n, out.ctypes.data_as(L._fp), None))
+        return out
+
+    # -- Tracker::WarpFunction(Mat, SE3, int), Tracker.cpp:1417 ------------------------------
+    def WarpFunction(self, points, pose7, lvl):
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+        pose = np.ascontiguousarray(pose7, np.float32)
+        out = np.empty_like(pts)
+        self._check(self._lib.uwt_warp_points(self._h, pts.ctypes.data_as(L._fp), pts.shape[0],
+                                              pose.ctypes.data_as(L._fp), lvl,
+                                              out.ctypes.data_as(L._fp)))
+        return out
+
+    def synchronize(self):
+        self._check(self._lib.uwt_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.uwt_launch_count(self._h))
+
+    # -- read-back accessors ------------------------------------------------------------------
+    def get_image(self, slot, lvl):
+        i = self.level_info(lvl)
+        out = np.empty((i.height, i.width), np.uint8)
+        self._check(self._lib.uwt_get_image(self._h, slot, lvl, out.ctypes.data_as(L._u8p)))
+        return out
+
+    def get_gradients(self, slot, lvl):
+        i = self.level_info(lvl)
+        gx = np.empty((i.height, i.width), np.int16)
+        gy = np.empty((i.height, i.width), np.int16)
+        g = np.empty((i.height, i.width), np.uint8)
+        self._check(self._lib.uwt_get_gradients(self._h, slot, lvl, gx.ctypes.data_as(L._i16p),
+                                                gy.ctypes.data_as(L._i16p),
+                                                g.ctypes.data_as(L._u8p)))
+        return gx, gy, g
+
+    def get_candidates(self, slot, lvl):
+        n = C.c_int(0)
+        self._check(self._lib.uwt_get_candidate_count(self._h, slot, lvl, C.byref(n)))
+        pts = np.empty((max(n.value, 1), 4), np.float32)
+        self._check(self._lib.uwt_get_candidates(self._h, slot, lvl, pts.ctypes.data_as(L._fp),
+                                                 pts.shape[0], C.byref(n)))
+        return pts[:n.value]
+
+    def get_trace(self, index=0, cap=512):
+        buf = (L.IterTrace * cap)()
+        n = C.c_int(0)
+        self._check(self._lib.uwt_get_trace(self._h, index, buf, cap, C.byref(n)))
+        return [buf[i] for i in range(n.value)]
+
+    @staticmethod
+    def _as_slots(frames):
+        if isinstance(frames, Frame):
+            return [frames.slot]
+        if isinstance(frames, (list, tuple)) and frames and isinstance(frames[0], Frame):
+            return [f.slot for f in frames]
+        return frames
+
+    @staticmethod
+    def _as_frames(frames):
+        if isinstance(frames, Frame):
+            return [frames]
+        if isinstance(frames, (list, tuple)) and frames and isinstance(frames[0], Frame):
+            return list(frames)
+        return []
