@@ -152,6 +152,18 @@ int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 long long uwt_launch_count(const uwt_tracker* t);
 
+/* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's
+ * roofline numbers).  Classes: */
+#define UWT_K_PYRAMID 0    /* K1 pyramid                          */
+#define UWT_K_GRADIENT 1   /* K2 Scharr + gradient image + sum    */
+#define UWT_K_CANDIDATES 2 /* K3 count + scan + scatter           */
+#define UWT_K_ESTIMATE 3   /* K4/K5 Gauss-Newton pose estimate    */
+#define UWT_K_COUNT 4
+/* on != 0: start (and reset) timing of every subsequent kernel class call; 0: stop. */
+int uwt_profile_enable(uwt_tracker* t, int on);
+/* Synchronises and returns the accumulated milliseconds and kernel launches per class. */
+int uwt_profile_read(uwt_tracker* t, double ms[UWT_K_COUNT], long long launches[UWT_K_COUNT]);
+
 #ifdef __cplusplus
 }
 #endif

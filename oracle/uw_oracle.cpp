@@ -683,4 +683,80 @@ int uwo_track_pair(const uwo_params* p, const uint8_t* prev0, const uint8_t* cur
   return rc;
 }
 
+
+// One reference-shaped tracking loop over a frame sequence (System::AddFrame +
+// System::Tracking in the direct order).  Frame 0 is only prepared; every
+// later frame i costs exactly one "track": pyramid(i), EstimatePose(i-1, i),
+// ApplyGradient(i), ObtainCandidatePoints(i).  poses_out: (n_frames-1) x 7;
+// seconds_out (optional): per-track wall seconds, (n_frames-1) entries.
+int uwo_track_sequence(const uwo_params* p, const uint8_t* frames, int n_frames,
+                       float* poses_out, double* seconds_out, uwo_stats* stats_out) {
+  const int L = p->levels;
+  struct FrameBuf {
+    std::vector<std::vector<uint8_t>> img, g;
+    std::vector<std::vector<int16_t>> gx, gy;
+    std::vector<std::vector<float>> cand;
+    std::vector<int> ncand;
+  };
+  auto prepare_pyr = [&](FrameBuf& f, const uint8_t* l0) {
+    f.img.resize(L);
+    for (int l = 0; l < L; ++l) {
+      const size_t n = (size_t)(p->width >> l) * (p->height >> l);
+      f.img[l].resize(n);
+      if (l == 0)
+        std::memcpy(f.img[0].data(), l0, n);
+      else
+        uwo_pyr_down(f.img[l - 1].data(), p->width >> (l - 1), p->height >> (l - 1),
+                     f.img[l].data());
+    }
+  };
+  auto prepare_grad = [&](FrameBuf& f) {
+    f.g.resize(L); f.gx.resize(L); f.gy.resize(L); f.cand.resize(L); f.ncand.assign(L, 0);
+    for (int l = 0; l < L; ++l) {
+      const int w = p->width >> l, h = p->height >> l;
+      f.gx[l].resize((size_t)w * h);
+      f.gy[l].resize((size_t)w * h);
+      f.g[l].resize((size_t)w * h);
+      uwo_scharr(f.img[l].data(), w, h, f.gx[l].data(), f.gy[l].data());
+      uwo_gradmag(f.gx[l].data(), f.gy[l].data(), (long long)w * h, f.g[l].data());
+    }
+    for (int l = 0; l < L; ++l) {
+      const int w = p->width >> l, h = p->height >> l;
+      f.cand[l].resize((size_t)w * h * 4);
+      f.ncand[l] = uwo_candidates(f.g[l].data(), w, h, p->gradient_threshold, f.cand[l].data(),
+                                  nullptr, nullptr);
+    }
+  };
+  const size_t fsz = (size_t)p->width * p->height;
+  FrameBuf a, b;
+  FrameBuf* prev = &a;
+  FrameBuf* cur = &b;
+  prepare_pyr(*prev, frames);
+  prepare_grad(*prev);
+  for (int i = 1; i < n_frames; ++i) {
+    const double t0 = now_s();
+    prepare_pyr(*cur, frames + (size_t)i * fsz);
+    const uint8_t* pp[UWO_MAX_LEVELS];
+    const uint8_t* cp[UWO_MAX_LEVELS];
+    const int16_t* gxp[UWO_MAX_LEVELS];
+    const int16_t* gyp[UWO_MAX_LEVELS];
+    const float* cd[UWO_MAX_LEVELS];
+    for (int l = 0; l < L; ++l) {
+      pp[l] = prev->img[l].data();
+      cp[l] = cur->img[l].data();
+      gxp[l] = prev->gx[l].data();
+      gyp[l] = prev->gy[l].data();
+      cd[l] = prev->cand[l].data();
+    }
+    int rc = uwo_estimate_pose(p, pp, cp, gxp, gyp, cd, prev->ncand.data(), nullptr,
+                               poses_out + (size_t)(i - 1) * 7,
+                               stats_out ? stats_out + (i - 1) : nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+    prepare_grad(*cur);
+    if (seconds_out) seconds_out[i - 1] = now_s() - t0;
+    std::swap(prev, cur);
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -116,6 +116,12 @@ int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
 int uwo_track_pair(const uwo_params* p, const uint8_t* prev0, const uint8_t* cur0,
                    float* out_pose7, uwo_stats* stats, double* seconds4);
 
+/* Reference-shaped loop over a sequence of n_frames level-0 frames (contiguous, w*h bytes
+ * each): one "track" per frame after the first = pyramid(i), EstimatePose(i-1,i),
+ * ApplyGradient(i), ObtainCandidatePoints(i).  poses_out: (n_frames-1) x 7. */
+int uwo_track_sequence(const uwo_params* p, const uint8_t* frames, int n_frames,
+                       float* poses_out, double* seconds_out, uwo_stats* stats_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,3 +275,22 @@ def track_pair(params, prev0, cur0):
     if rc != 0:
         raise RuntimeError("uwo_track_pair failed: %d" % rc)
     return out, st, list(secs)
+
+
+def track_sequence(params, frames):
+    """frames: u8 [n, H, W].  Returns (poses [n-1, 7], seconds [n-1], [Stats])."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n = frames.shape[0]
+    poses = np.empty((n - 1, 7), np.float32)
+    secs = np.empty(n - 1, np.float64)
+    stats = (Stats * (n - 1))()
+    L = lib()
+    L.uwo_track_sequence.restype = C.c_int
+    L.uwo_track_sequence.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint8), C.c_int,
+                                     C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                     C.POINTER(Stats)]
+    rc = L.uwo_track_sequence(C.byref(params), _p(frames, C.c_uint8), n, _p(poses, C.c_float),
+                              _p(secs, C.c_double), stats)
+    if rc != 0:
+        raise RuntimeError("uwo_track_sequence failed: %d" % rc)
+    return poses, secs, list(stats)

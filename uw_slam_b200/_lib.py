@@ -11,6 +11,7 @@ MAX_LEVELS = 7
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
 SOLVE_LU, SOLVE_INVERSE = 0, 1
 FLAG_TRACE = 1
+KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 
 
 class Config(C.Structure):
@@ -72,6 +73,8 @@ SIGNATURES = {
     "uwt_get_candidates": (C.c_int, [_H, C.c_int, C.c_int, _fp, C.c_int, _ip]),
     "uwt_get_trace": (C.c_int, [_H, C.c_int, C.POINTER(IterTrace), C.c_int, _ip]),
     "uwt_launch_count": (C.c_longlong, [_H]),
+    "uwt_profile_enable": (C.c_int, [_H, C.c_int]),
+    "uwt_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

@@ -59,6 +59,12 @@ struct uwt_tracker {
   int max_cluster = 1;
   long long launches = 0;
   std::string error;
+  // optional per-kernel-class event timing
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int cls; cudaEvent_t a, b; int launches; };
+  std::vector<Span> spans;
 };
 
 namespace {
@@ -84,6 +90,36 @@ int fail(uwt_tracker* t, int code, const char* fmt, ...) {
   } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+cudaEvent_t prof_event(uwt_tracker* t) {
+  if (t->ev_used == t->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    t->ev_pool.push_back(e);
+  }
+  return t->ev_pool[t->ev_used++];
+}
+
+// RAII span: records an event pair around one kernel-class call when profiling is on.
+struct ProfSpan {
+  uwt_tracker* t;
+  int cls;
+  cudaEvent_t a = nullptr;
+  ProfSpan(uwt_tracker* t_, int cls_) : t(t_), cls(cls_) {
+    if (t->profiling) {
+      a = prof_event(t);
+      cudaEventRecord(a, t->stream);
+    }
+  }
+  void done(int launches) {
+    if (a) {
+      cudaEvent_t b = prof_event(t);
+      cudaEventRecord(b, t->stream);
+      t->spans.push_back({cls, a, b, launches});
+      a = nullptr;
+    }
+  }
+};
 
 int build_geom(const uwt_config& c, Geom& g) {
   std::memset(&g, 0, sizeof(g));
@@ -189,6 +225,7 @@ void destroy_impl(uwt_tracker* t) {
   cudaFree(p.img); cudaFree(p.gx); cudaFree(p.gy); cudaFree(p.g); cudaFree(p.gpart);
   cudaFree(p.ticket); cudaFree(p.ithr); cudaFree(p.cnt); cudaFree(p.ncand);
   cudaFree(p.cand_xy); cudaFree(p.rec);
+  for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   for (ArgRegion& r : t->ring) {
     if (r.h_int) cudaFreeHost(r.h_int);
     if (r.h_flt) cudaFreeHost(r.h_flt);
@@ -375,6 +412,33 @@ int uwt_synchronize(uwt_tracker* t) {
 
 long long uwt_launch_count(const uwt_tracker* t) { return t ? t->launches : 0; }
 
+int uwt_profile_enable(uwt_tracker* t, int on) {
+  if (!t) return UWT_E_INVALID;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  t->profiling = on != 0;
+  t->spans.clear();
+  t->ev_used = 0;
+  return UWT_OK;
+}
+
+int uwt_profile_read(uwt_tracker* t, double ms[UWT_K_COUNT], long long launches[UWT_K_COUNT]) {
+  if (!t || !ms || !launches) return UWT_E_INVALID;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  for (int i = 0; i < UWT_K_COUNT; ++i) {
+    ms[i] = 0.0;
+    launches[i] = 0;
+  }
+  for (const uwt_tracker::Span& s : t->spans) {
+    float v = 0.f;
+    UWT_CUDA(t, cudaEventElapsedTime(&v, s.a, s.b));
+    ms[s.cls] += v;
+    launches[s.cls] += s.launches;
+  }
+  return UWT_OK;
+}
+
 static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t* dev_src,
                           size_t row_stride, size_t frame_stride) {
   ArgRegion* r;
@@ -382,8 +446,10 @@ static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t
   if (rc) return rc;
   rc = push_slots(t, r, n, slots, nullptr);
   if (rc) return rc;
+  ProfSpan span(t, UWT_K_PYRAMID);
   const int k = launch_pyramid(t->geom, t->pools, n, r->d_int, dev_src, row_stride, frame_stride,
                                false, t->stream);
+  span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "pyramid kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
   t->launches += k;
@@ -444,7 +510,9 @@ int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {
   ArgRegion* r;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
+  ProfSpan span(t, UWT_K_GRADIENT);
   const int k = launch_gradient(t->geom, t->pools, n, r->d_int, t->stream);
+  span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "gradient kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
   t->launches += k;
@@ -466,7 +534,9 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
   ArgRegion* r;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
+  ProfSpan span(t, UWT_K_CANDIDATES);
   const int k = launch_candidates(t->geom, t->pools, n, r->d_int, t->stream);
+  span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "candidate kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
   t->launches += k;
@@ -516,6 +586,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   io.trace_count = tracing ? t->d_trace_count : nullptr;
   io.trace_cap = t->trace_cap;
   int cluster = pick_cluster(t, n);
+  ProfSpan span(t, UWT_K_ESTIMATE);
   int k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream);
   while (k < 0 && cluster > 1) {  // a 16-CTA cluster may not be schedulable on every part
     cudaGetLastError();
@@ -526,6 +597,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   if (k < 0) return fail(t, UWT_E_CUDA, "estimate kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
   t->launches += k;
+  span.done(k);
   UWT_CUDA(t, cudaMemcpyAsync(t->h_out_poses, t->d_out_poses, sizeof(float) * 7 * n,
                               cudaMemcpyDeviceToHost, t->stream));
   UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, t->d_stats, sizeof(uwt_track_stats) * n,

@@ -233,6 +233,19 @@ class Tracker:
     def launch_count(self):
         return int(self._lib.uwt_launch_count(self._h))
 
+    def profile(self, on=True):
+        self._check(self._lib.uwt_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} accumulated since profile(True)."""
+        ms = (C.c_double * len(L.KERNEL_CLASSES))()
+        ln = (C.c_longlong * len(L.KERNEL_CLASSES))()
+        self._check(self._lib.uwt_profile_read(self._h, ms, ln))
+        return {k: (ms[i], int(ln[i])) for i, k in enumerate(L.KERNEL_CLASSES)}
+
+    def stream_ptr(self):
+        return int(self._lib.uwt_stream(self._h) or 0)
+
     # -- read-back accessors ------------------------------------------------------------------
     def get_image(self, slot, lvl):
         i = self.level_info(lvl)
