@@ -213,6 +213,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import uw_slam_b200 as U
+    from uw_slam_b200 import _lib as L
 
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -221,7 +222,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     w, h, fx, fy, cx, cy = synth.CALIB[CALIB]
     B, K, W = args.batch, args.steps, args.warmup
-    n_frames = 1 + W + K
+    n_frames = 1 + W + K + 1  # +1: the e2e loop uploads one frame ahead
 
     # ---- synthetic sequences (device + pinned host copies) ----
     seeds = [rank * 100_000 + i for i in range(B)]
@@ -232,7 +233,7 @@ def run_ours(args):
 
     t = U.Tracker(False)
     t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
-                        max_frames=2 * B, device=local_rank)
+                        max_frames=2 * B, device=local_rank, cluster_size=args.cluster)
     stream = torch.cuda.ExternalStream(t.stream_ptr(), device=dev)
     slots_a, slots_b = list(range(B)), list(range(B, 2 * B))
     frame_bytes = w * h
@@ -242,29 +243,44 @@ def run_ours(args):
         t.ApplyGradient(slots_a)
         t.ObtainCandidatePoints(slots_a)
 
-    def step(i, prev, cur, from_host):
+    def upload(i, cur, from_host):
         if from_host:
             t.AddFramesHostPtr(cur, host[i].data_ptr(), w, frame_bytes)
         else:
             t.AddFramesDevice(cur, frames[i].data_ptr())
+
+    def track(prev, cur):
         t.EstimatePoseAsync(prev, cur)
         t.ApplyGradient(cur)
         t.ObtainCandidatePoints(cur)
 
     def barrier():
+        t.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(from_host, fetch):
+    def fetch():
+        st = (L.TrackStats * B)()
+        out = np.empty((B, 7), np.float32)
+        t._check(t._lib.uwt_fetch_poses(t._h, B, out.ctypes.data_as(L._fp), st))
+        return out, st
+
+    def timed_loop(from_host, fetch_poses):
+        """Software-pipelined: the frames of step i+1 are handed to the library (H2D on its
+        copy stream when they come from the host) while step i is still being tracked, and
+        the poses of step i are read after that.  Every timed step contains exactly one
+        upload, one track and (e2e) one pose read."""
         prime()
         prev, cur = slots_a, slots_b
         stats_acc = []
+        upload(1, cur, from_host)
         for i in range(1, 1 + W):
-            step(i, prev, cur, from_host)
-            if fetch:
-                t.FetchPoses(B)
+            track(prev, cur)
+            upload(i + 1, prev, from_host)   # next step's frames go where `prev` lives
+            if fetch_poses:
+                fetch()
             prev, cur = cur, prev
         barrier()
         t.profile(True)
@@ -276,14 +292,10 @@ def run_ours(args):
         wall0 = time.perf_counter()
         e0.record(stream)
         for i in range(1 + W, 1 + W + K):
-            step(i, prev, cur, from_host)
-            if fetch:
-                import ctypes as C
-                from uw_slam_b200 import _lib as L
-                st = (L.TrackStats * B)()
-                out = np.empty((B, 7), np.float32)
-                t._check(t._lib.uwt_fetch_poses(t._h, B, out.ctypes.data_as(L._fp), st))
-                stats_acc.append((out, st))
+            track(prev, cur)
+            upload(i + 1, prev, from_host)
+            if fetch_poses:
+                stats_acc.append(fetch())
             prev, cur = cur, prev
         e1.record(stream)
         barrier()
@@ -300,9 +312,9 @@ def run_ours(args):
         return ms, wall, prof, launches, clocks, stats_acc
 
     # ---- value: inputs resident in HBM ----
-    ms, wall, prof, launches, clocks, _ = timed_loop(from_host=False, fetch=False)
+    ms, wall, prof, launches, clocks, _ = timed_loop(from_host=False, fetch_poses=False)
     # ---- e2e: pinned host frames in, poses out, every step ----
-    ms_e, wall_e, prof_e, launches_e, clocks_e, stats_acc = timed_loop(from_host=True, fetch=True)
+    ms_e, wall_e, prof_e, launches_e, clocks_e, stats_acc = timed_loop(from_host=True, fetch_poses=True)
 
     # algorithmic bytes of the estimate kernel: 10 B x points x residual sweeps (both loops
     # process the same frames, so the sweeps counted in the e2e loop hold for the value loop)
@@ -349,6 +361,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (%.0f MB of new frames + %.1f GB "
                                     "working set per step)" % (B * n0 / 1e6,
                                                                  2 * B * 21e6 / 1e9),
+                       "cluster_size": args.cluster,
                        "parallelism": "independent sequences, %d per GPU, no comms" % B},
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": ms_e / K,
                     "h2d_bytes_per_step": B * n0, "d2h_bytes_per_step":
@@ -367,12 +380,12 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             # bounded CPU sample of the same workload: the first `nseq` sequences, all K+W steps
             nseq = min(B, args.cpu_sequences)
-            fr = host[:, :nseq].permute(1, 0, 2, 3).contiguous().numpy()
+            fr = host[:1 + W + K, :nseq].permute(1, 0, 2, 3).contiguous().numpy()
             n, dt, poses = cpu_tracks(fr, 1)
             line["cpu_baseline"] = {
                 "value": n / dt, "unit": "tracks/s", "cores": 1, "kind": "port",
                 "sample": "%d sequences x %d frames of this workload (%d tracks, %.1f s), "
-                          "single-threaded oracle" % (nseq, n_frames, n, dt)}
+                          "single-threaded oracle" % (nseq, 1 + W + K, n, dt)}
             # bonus: the oracle's last pose of every sampled sequence vs the GPU's e2e result
             gpu_last = stats_acc[-1][0]
             same = all(np.array_equal(poses[s][-1], gpu_last[s]) for s in range(nseq))
@@ -392,6 +405,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="sequences per GPU")
+    ap.add_argument("--cluster", type=int, default=0, help="CTAs per problem (0 = auto)")
     ap.add_argument("--cpu-sequences", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -112,7 +112,9 @@ int uwt_synchronize(uwt_tracker* t);
 
 /* System::AddFrame: copy n gray frames from HOST memory (frame i at host + i*frame_stride,
  * rows row_stride bytes apart) into slots[i] and build their pyramids.  Asynchronous with
- * respect to the host when `host` is pinned; resets the slots' gradient/candidate state. */
+ * respect to the host when `host` is pinned (the buffer must stay valid until the copy has
+ * run); the copy uses its own stream and double-buffered staging, so it overlaps kernels
+ * already enqueued on the handle.  Resets the slots' gradient/candidate state. */
 int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* host,
                       size_t row_stride, size_t frame_stride);
 /* Same, from frames already resident in DEVICE memory. */
@@ -130,8 +132,9 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots);
  * prev->rigid_transformation_; stats (n entries, host) may be NULL.  Synchronous. */
 int uwt_estimate_pose(uwt_tracker* t, int n, const int* prev_slots, const int* cur_slots,
                       const float* init_poses7, float* out_poses7, uwt_track_stats* stats);
-/* Asynchronous form: results land in library-owned pinned memory after uwt_synchronize;
- * fetch them with uwt_fetch_poses.  Lets the host overlap uploads with tracking. */
+/* Asynchronous form: results land in library-owned pinned memory; uwt_fetch_poses waits for
+ * this estimate only (not for work enqueued after it) and copies them out.  Lets the host
+ * enqueue the next upload before reading the poses of the current batch. */
 int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots,
                             const int* cur_slots, const float* init_poses7);
 int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* stats);

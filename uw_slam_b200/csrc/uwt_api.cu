@@ -46,8 +46,16 @@ struct uwt_tracker {
   std::vector<SlotState> slots;
   ArgRegion ring[kRing];
   int ring_next = 0;
-  uint8_t* d_stage = nullptr;  // upload staging
+  // upload path: H2D copies run on their own stream into one of two staging buffers so that
+  // the copy of the next batch overlaps the kernels of the current one
+  cudaStream_t copy_stream = nullptr;
+  uint8_t* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr};  // recorded on copy_stream after the H2D
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};   // recorded on stream after the pyramid
+  bool stage_busy[2] = {false, false};
+  int stage_next = 0;
   size_t stage_frames = 0;
+  cudaEvent_t poses_ready = nullptr;  // recorded after the D2H of the last estimate
   float* d_out_poses = nullptr;
   uwt_track_stats* d_stats = nullptr;
   float* h_out_poses = nullptr;       // pinned
@@ -220,6 +228,7 @@ int push_slots(uwt_tracker* t, ArgRegion* r, int n, const int* a, const int* b) 
 void destroy_impl(uwt_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->cfg.device);
+  if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   if (t->stream) cudaStreamSynchronize(t->stream);
   Pools& p = t->pools;
   cudaFree(p.img); cudaFree(p.gx); cudaFree(p.gy); cudaFree(p.g); cudaFree(p.gpart);
@@ -233,7 +242,13 @@ void destroy_impl(uwt_tracker* t) {
     cudaFree(r.d_flt);
     if (r.ev) cudaEventDestroy(r.ev);
   }
-  cudaFree(t->d_stage);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(t->d_stage[i]);
+    if (t->stage_ready[i]) cudaEventDestroy(t->stage_ready[i]);
+    if (t->stage_free[i]) cudaEventDestroy(t->stage_free[i]);
+  }
+  if (t->poses_ready) cudaEventDestroy(t->poses_ready);
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   cudaFree(t->d_out_poses);
   cudaFree(t->d_stats);
   cudaFree(t->d_trace);
@@ -325,6 +340,7 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   } while (0)
   CREATE_CUDA(cudaSetDevice(c.device));
   CREATE_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
   const Geom& g = t->geom;
   const size_t F = (size_t)c.max_frames;
   Pools& p = t->pools;
@@ -353,7 +369,12 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   }
   const size_t frame_bytes = (size_t)c.width * c.height;
   t->stage_frames = std::max<size_t>(1, std::min<size_t>(F, ((size_t)256 << 20) / frame_bytes));
-  CREATE_CUDA(cudaMalloc(&t->d_stage, t->stage_frames * frame_bytes));
+  for (int i = 0; i < 2; ++i) {
+    CREATE_CUDA(cudaMalloc(&t->d_stage[i], t->stage_frames * frame_bytes));
+    CREATE_CUDA(cudaEventCreateWithFlags(&t->stage_ready[i], cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&t->stage_free[i], cudaEventDisableTiming));
+  }
+  CREATE_CUDA(cudaEventCreateWithFlags(&t->poses_ready, cudaEventDisableTiming));
   CREATE_CUDA(cudaMalloc(&t->d_out_poses, sizeof(float) * 7 * F));
   CREATE_CUDA(cudaMalloc(&t->d_stats, sizeof(uwt_track_stats) * F));
   CREATE_CUDA(cudaHostAlloc(&t->h_out_poses, sizeof(float) * 7 * F, cudaHostAllocDefault));
@@ -406,6 +427,7 @@ void* uwt_stream(const uwt_tracker* t) { return t ? (void*)t->stream : nullptr; 
 int uwt_synchronize(uwt_tracker* t) {
   if (!t) return UWT_E_INVALID;
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  UWT_CUDA(t, cudaStreamSynchronize(t->copy_stream));
   UWT_CUDA(t, cudaStreamSynchronize(t->stream));
   return UWT_OK;
 }
@@ -474,17 +496,27 @@ int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* ho
   for (size_t done = 0; done < (size_t)n;) {
     const size_t cnt = std::min(t->stage_frames, (size_t)n - done);
     const uint8_t* src = host + done * frame_stride;
+    const int sb = t->stage_next;
+    t->stage_next ^= 1;
+    // the copy engine may refill this staging buffer once the pyramid kernel that last read
+    // it has finished
+    if (t->stage_busy[sb]) UWT_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->stage_free[sb], 0));
+    uint8_t* stage = t->d_stage[sb];
     if (frame_stride == row_stride * h) {
       // frames are contiguous: one strided copy for the whole chunk
-      UWT_CUDA(t, cudaMemcpy2DAsync(t->d_stage, w, src, row_stride, w, h * cnt,
-                                    cudaMemcpyHostToDevice, t->stream));
+      UWT_CUDA(t, cudaMemcpy2DAsync(stage, w, src, row_stride, w, h * cnt,
+                                    cudaMemcpyHostToDevice, t->copy_stream));
     } else {
       for (size_t i = 0; i < cnt; ++i)
-        UWT_CUDA(t, cudaMemcpy2DAsync(t->d_stage + i * w * h, w, src + i * frame_stride,
-                                      row_stride, w, h, cudaMemcpyHostToDevice, t->stream));
+        UWT_CUDA(t, cudaMemcpy2DAsync(stage + i * w * h, w, src + i * frame_stride, row_stride,
+                                      w, h, cudaMemcpyHostToDevice, t->copy_stream));
     }
-    rc = pyramid_common(t, (int)cnt, slots + done, t->d_stage, w, w * h);
+    UWT_CUDA(t, cudaEventRecord(t->stage_ready[sb], t->copy_stream));
+    UWT_CUDA(t, cudaStreamWaitEvent(t->stream, t->stage_ready[sb], 0));
+    rc = pyramid_common(t, (int)cnt, slots + done, stage, w, w * h);
     if (rc) return rc;
+    UWT_CUDA(t, cudaEventRecord(t->stage_free[sb], t->stream));
+    t->stage_busy[sb] = true;
     done += cnt;
   }
   return UWT_OK;
@@ -548,9 +580,11 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
 static int pick_cluster(const uwt_tracker* t, int n) {
   int c = t->cfg.cluster_size;
   if (c == 0) {
-    // fill the 148 SMs: one CTA per problem for large batches, a 16-CTA cluster for one
+    // Aim for >= 4 CTAs per SM-slot so the tail of unequal problems (different iteration
+    // counts) averages out: one CTA per problem only for very large batches, a 16-CTA
+    // cluster for a single problem.
     c = 1;
-    while (c < 16 && n * c * 2 <= 148) c *= 2;
+    while (c < 16 && n * c < 4 * 148) c *= 2;
   }
   return std::min(c, t->max_cluster);
 }
@@ -602,6 +636,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
                               cudaMemcpyDeviceToHost, t->stream));
   UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, t->d_stats, sizeof(uwt_track_stats) * n,
                               cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaEventRecord(t->poses_ready, t->stream));
   if ((rc = release(t, r))) return rc;
   t->last_n = n;
   return UWT_OK;
@@ -611,7 +646,8 @@ int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* s
   if (!t) return UWT_E_INVALID;
   if (n <= 0 || n > t->last_n) return fail(t, UWT_E_INVALID, "n=%d exceeds the last batch (%d)", n, t->last_n);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  // waits for the estimate + its D2H only, not for work enqueued after it
+  UWT_CUDA(t, cudaEventSynchronize(t->poses_ready));
   if (out_poses7) std::memcpy(out_poses7, t->h_out_poses, sizeof(float) * 7 * n);
   if (stats) std::memcpy(stats, t->h_stats, sizeof(uwt_track_stats) * n);
   return UWT_OK;

@@ -5,25 +5,27 @@
 // the selected pixels with x as the OUTER and y as the INNER loop (Tracker.cpp:1334-1335).
 //
 // Stream compaction in that (column-major) order over row-major images:
-//   count   : one warp per (128-column strip, 32-row segment); lane = 4 columns (one 32-bit
-//             load per row, 128 B per warp request); per-(column, segment) counts
+//   count   : one CTA per (128-column strip, 64-row segment): the tile of the gradient
+//             image is read row-wise (coalesced 128 B per warp request) into shared memory,
+//             then every warp walks whole columns of the tile (lane = row, padded pitch =
+//             conflict-free), thresholds, ballots and popcounts -> per-(column, segment)
+//             counts
 //   scan    : one CTA per (slot, level): exclusive prefix sum over (column major, segment
 //             minor) -> start offset of every (column, segment) run; total = N_l
-//   scatter : same decomposition as count; each lane walks its 4 columns down the segment
-//             and appends (x, y) -- and, on the levels EstimatePose optimises, the packed
-//             8-byte record (x, y, I1, gx, gy) the Gauss-Newton kernel streams.
+//   scatter : same tiles as count; a warp handles one column x 32 rows per step, so the
+//             selected points of a column are appended with ONE coalesced store per step
+//             (ballot + popc prefix): (x, y) -- and, on the levels EstimatePose optimises,
+//             the packed 8-byte record (x, y, I1, gx, gy) the Gauss-Newton kernel streams.
 #include "uwt_internal.cuh"
 
 namespace uwt {
 
-struct WarpItem {
+struct TileItem {
   int lvl, strip, seg;
-  bool valid;
 };
 
-__device__ __forceinline__ WarpItem locate_item(const Geom& geom, int item) {
-  WarpItem w;
-  w.valid = false;
+__device__ __forceinline__ TileItem locate_item(const Geom& geom, int item) {
+  TileItem w;
   w.lvl = w.strip = w.seg = 0;
   for (int l = 0; l < geom.levels; ++l) {
     const int cnt = geom.lv[l].nstrip * geom.lv[l].nseg;
@@ -31,7 +33,6 @@ __device__ __forceinline__ WarpItem locate_item(const Geom& geom, int item) {
       w.lvl = l;
       w.strip = item % geom.lv[l].nstrip;
       w.seg = item / geom.lv[l].nstrip;
-      w.valid = true;
       return w;
     }
     item -= cnt;
@@ -39,28 +40,67 @@ __device__ __forceinline__ WarpItem locate_item(const Geom& geom, int item) {
   return w;
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kTilePitch8 = kStripW + 4;    // bytes per u8 tile row: 33 words -> no conflicts
+constexpr int kTilePitch16 = kStripW + 2;   // int16 per tile row: 65 words -> no conflicts
+
+// Loads the (kSegRows x kStripW) u8 tile at (x0, y0) row-wise into shared memory.
+__device__ __forceinline__ void load_tile_u8(const uint8_t* __restrict__ plane, const LevelGeom& L,
+                                             int x0, int y0, uint8_t* tile, int t) {
+  const int lane = t & 31, wid = t >> 5;
+  const int gx = x0 + lane * 4;
+#pragma unroll
+  for (int j = 0; j < kSegRows / 8; ++j) {
+    const int row = wid + 8 * j, gy = y0 + row;
+    uint32_t v = 0;
+    if (gy < L.h && gx < L.pitch) v = *reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx);
+    *reinterpret_cast<uint32_t*>(tile + row * kTilePitch8 + lane * 4) = v;
+  }
+}
+
+__device__ __forceinline__ void load_tile_i16(const int16_t* __restrict__ plane, const LevelGeom& L,
+                                              int x0, int y0, int16_t* tile, int t) {
+  const int lane = t & 31, wid = t >> 5;
+  const int gx = x0 + lane * 4;
+#pragma unroll
+  for (int j = 0; j < kSegRows / 8; ++j) {
+    const int row = wid + 8 * j, gy = y0 + row;
+    uint2 v = make_uint2(0, 0);
+    if (gy < L.h && gx < L.pitch) v = *reinterpret_cast<const uint2*>(plane + (size_t)gy * L.pitch + gx);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tile + row * kTilePitch16 + lane * 4);
+    d[0] = v.x;
+    d[1] = v.y;
+  }
+}
+
+__global__ void __launch_bounds__(256)
 cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
                   const int* __restrict__ slots) {
-  const int lane = threadIdx.x & 31;
-  const WarpItem it = locate_item(geom, blockIdx.x * 4 + (threadIdx.x >> 5));
-  if (!it.valid) return;
+  __shared__ __align__(16) uint8_t sg[kSegRows * kTilePitch8];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const TileItem it = locate_item(geom, blockIdx.x);
   const int slot = slots[blockIdx.y];
   const LevelGeom& L = geom.lv[it.lvl];
-  const int x = it.strip * kStripW + lane * 4;
-  if (x >= L.w) return;
-  const int nvalid = min(4, L.w - x);
-  const int y_lo = it.seg * kSegRows, y_hi = min(y_lo + kSegRows, L.h);
+  const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
   const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
-  const uint8_t* g = pools.g + (size_t)slot * geom.plane_elems + L.plane_off + x;
-  uint32_t c[4] = {0, 0, 0, 0};
-  for (int y = y_lo; y < y_hi; ++y) {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(g + (size_t)y * L.pitch);
+  load_tile_u8(pools.g + (size_t)slot * geom.plane_elems + L.plane_off, L, x0, y0, sg, t);
+  __syncthreads();
+  // warp `wid` owns tile columns [16 wid, 16 wid + 16); lane = row within a 32-row chunk
+  uint32_t mine = 0;
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const int c = wid * 16 + j;
+    uint32_t cnt = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] += (((v >> (8 * i)) & 0xFFu) > ithr) ? 1u : 0u;
+    for (int ch = 0; ch < kSegRows / 32; ++ch) {
+      const int row = ch * 32 + lane;
+      const bool sel = (y0 + row < L.h) && ((uint32_t)sg[row * kTilePitch8 + c] > ithr);
+      cnt += __popc(__ballot_sync(0xffffffffu, sel));
+    }
+    if (lane == j) mine = cnt;
   }
-  uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
-  for (int i = 0; i < nvalid; ++i) cnt[(size_t)(x + i) * L.nseg + it.seg] = c[i];
+  const int x = x0 + wid * 16 + lane;
+  if (lane < 16 && x < L.w)
+    pools.cnt[(size_t)slot * geom.cnt_elems + L.cnt_off + (size_t)x * L.nseg + it.seg] = mine;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -105,77 +145,78 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
   if (t == 1023) pools.ncand[(size_t)slot * kMaxLevels + lvl] = warp_tot[31];
 }
 
-__global__ void __launch_bounds__(128)
+constexpr size_t kScatterSmem =
+    2 * (size_t)kSegRows * kTilePitch8 + 2 * (size_t)kSegRows * kTilePitch16 * sizeof(int16_t);
+
+__global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
                     const int* __restrict__ slots) {
-  const int lane = threadIdx.x & 31;
-  const WarpItem it = locate_item(geom, blockIdx.x * 4 + (threadIdx.x >> 5));
-  if (!it.valid) return;
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint8_t* sg = smem;
+  uint8_t* si = sg + kSegRows * kTilePitch8;
+  int16_t* sgx = reinterpret_cast<int16_t*>(si + kSegRows * kTilePitch8);
+  int16_t* sgy = sgx + kSegRows * kTilePitch16;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const TileItem it = locate_item(geom, blockIdx.x);
   const int slot = slots[blockIdx.y];
   const LevelGeom& L = geom.lv[it.lvl];
-  const int x = it.strip * kStripW + lane * 4;
-  if (x >= L.w) return;
-  const int nvalid = min(4, L.w - x);
-  const int y_lo = it.seg * kSegRows, y_hi = min(y_lo + kSegRows, L.h);
+  const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
   const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
-  const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off + x;
-  const uint8_t* g = pools.g + pbase;
-  const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
-  uint32_t cur[4] = {0, 0, 0, 0};
-  for (int i = 0; i < nvalid; ++i) cur[i] = cnt[(size_t)(x + i) * L.nseg + it.seg];
-  uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
+  const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off;
   const bool has_rec = L.rec_off >= 0;
+  load_tile_u8(pools.g + pbase, L, x0, y0, sg, t);
+  if (has_rec) {
+    load_tile_u8(pools.img + pbase, L, x0, y0, si, t);
+    load_tile_i16(pools.gx + pbase, L, x0, y0, sgx, t);
+    load_tile_i16(pools.gy + pbase, L, x0, y0, sgy, t);
+  }
+  __syncthreads();
+  const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
+  uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
   uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
-  const uint8_t* img = pools.img + pbase;
-  const int16_t* gxp = pools.gx + pbase;
-  const int16_t* gyp = pools.gy + pbase;
-  const bool vec = (nvalid == 4);
-  for (int y = y_lo; y < y_hi; ++y) {
-    const size_t ro = (size_t)y * L.pitch;
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(g + ro);
-    uint32_t sel = 0;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // start offsets of this warp's 16 (column, segment) runs: one per lane
+  uint32_t my_base = 0;
+  {
+    const int x = x0 + wid * 16 + lane;
+    if (lane < 16 && x < L.w) my_base = cnt[(size_t)x * L.nseg + it.seg];
+  }
+#pragma unroll 2
+  for (int j = 0; j < 16; ++j) {
+    const int c = wid * 16 + j, x = x0 + c;
+    uint32_t base = __shfl_sync(0xffffffffu, my_base, j);
+    if (x >= L.w) break;  // warp-uniform
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (i < nvalid && ((v >> (8 * i)) & 0xFFu) > ithr) sel |= 1u << i;
-    if (!sel) continue;
-    uint32_t iv = 0;
-    int gxs[4] = {0, 0, 0, 0}, gys[4] = {0, 0, 0, 0};
-    if (has_rec) {
-      iv = *reinterpret_cast<const uint32_t*>(img + ro);
-      if (vec) {
-        const uint2 a = *reinterpret_cast<const uint2*>(gxp + ro);
-        const uint2 b = *reinterpret_cast<const uint2*>(gyp + ro);
-        gxs[0] = (short)(a.x & 0xFFFF); gxs[1] = (short)(a.x >> 16);
-        gxs[2] = (short)(a.y & 0xFFFF); gxs[3] = (short)(a.y >> 16);
-        gys[0] = (short)(b.x & 0xFFFF); gys[1] = (short)(b.x >> 16);
-        gys[2] = (short)(b.y & 0xFFFF); gys[3] = (short)(b.y >> 16);
-      } else {
-        for (int i = 0; i < nvalid; ++i) {
-          gxs[i] = gxp[ro + i];
-          gys[i] = gyp[ro + i];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (sel & (1u << i)) {
-        const uint32_t o = cur[i]++;
-        xy[o] = (uint32_t)(x + i) | ((uint32_t)y << 16);
+    for (int ch = 0; ch < kSegRows / 32; ++ch) {
+      const int row = ch * 32 + lane, y = y0 + row;
+      const bool sel = (y < L.h) && ((uint32_t)sg[row * kTilePitch8 + c] > ithr);
+      const uint32_t b = __ballot_sync(0xffffffffu, sel);
+      if (sel) {
+        const uint32_t o = base + __popc(b & lt_mask);
+        xy[o] = (uint32_t)x | ((uint32_t)y << 16);
         if (has_rec)
-          rec[o] = pack_record((uint32_t)(x + i), (uint32_t)y, (iv >> (8 * i)) & 0xFFu, gxs[i],
-                               gys[i]);
+          rec[o] = pack_record((uint32_t)x, (uint32_t)y, si[row * kTilePitch8 + c],
+                               sgx[row * kTilePitch16 + c], sgy[row * kTilePitch16 + c]);
       }
+      base += __popc(b);
     }
   }
 }
 
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st) {
-  dim3 grid((g.warp_items_total + 3) / 4, n);
-  cand_count_kernel<<<grid, 128, 0, st>>>(g, p, d_slots);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cand_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kScatterSmem) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  dim3 grid(g.warp_items_total, n);
+  cand_count_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
   cand_scan_kernel<<<dim3(g.levels, n), 1024, 0, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scatter_kernel<<<grid, 128, 0, st>>>(g, p, d_slots);
+  cand_scatter_kernel<<<grid, 256, kScatterSmem, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 3;
 }

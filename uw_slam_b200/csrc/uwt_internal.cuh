@@ -12,9 +12,9 @@ constexpr int kMaxLevels = UWT_MAX_LEVELS;
 // Gradient tile (K2): 128 x 32 pixels, staged with a 16-byte-aligned halo by cp.async.bulk.
 constexpr int kGradTileW = 128;
 constexpr int kGradTileH = 32;
-// Candidate compaction (K3): one warp owns a 128-column strip x kSegRows rows.
+// Candidate compaction (K3): one CTA owns a 128-column strip x kSegRows rows.
 constexpr int kStripW = 128;
-constexpr int kSegRows = 32;
+constexpr int kSegRows = 64;
 // Pyramid tile (K1): 64 x 64 level-0 pixels -> 32x32, 16x16, 8x8, 4x4, 2x2, 1x1.
 constexpr int kPyrTile = 64;
 
@@ -48,7 +48,7 @@ struct Geom {
   // per-slot strides (elements)
   size_t plane_elems, cand_elems, rec_elems, cnt_elems, tile_elems;
   int grad_tiles_total;  // gradient tiles per slot over all levels
-  int warp_items_total;  // compaction warp-items per slot over all levels
+  int warp_items_total;  // compaction tiles per slot over all levels
 };
 
 // Device memory pools, indexed [slot].
