@@ -580,11 +580,12 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
 static int pick_cluster(const uwt_tracker* t, int n) {
   int c = t->cfg.cluster_size;
   if (c == 0) {
-    // Aim for >= 4 CTAs per SM-slot so the tail of unequal problems (different iteration
-    // counts) averages out: one CTA per problem only for very large batches, a 16-CTA
-    // cluster for a single problem.
+    // Enough CTAs that the tail of unequal problems (different iteration counts) averages
+    // out over >= 2 CTAs per SM, but no more: every extra CTA of a cluster repeats the
+    // per-sweep table build / reduction / solve.  Measured on B200 (128 problems at
+    // 1280x1024): C=1 1.57 ms, 2 1.43, 4 1.22, 8 1.31, 16 1.86 per launch.
     c = 1;
-    while (c < 16 && n * c < 4 * 148) c *= 2;
+    while (c < 16 && n * c < 2 * 148) c *= 2;
   }
   return std::min(c, t->max_cluster);
 }
