@@ -85,7 +85,7 @@ typedef struct {
   float final_error[UWT_MAX_LEVELS];
 } uwt_track_stats;
 
-/* Same content as the oracle's trace record, one per residual sweep. */
+/* Per-sweep trace record (UWT_FLAG_TRACE): the quantities of one Gauss-Newton iteration. */
 typedef struct {
   int level, k, n_valid, broke;
   long long sum_r2;
