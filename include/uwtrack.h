@@ -138,6 +138,20 @@ int uwt_estimate_pose(uwt_tracker* t, int n, const int* prev_slots, const int* c
 int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots,
                             const int* cur_slots, const float* init_poses7);
 int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* stats);
+/* Single-huge-frame mode: the Gauss-Newton loop of ONE (prev, cur) pair split over `nranks`
+ * handles, one per GPU (each holds both frames; rank r sweeps the r-th contiguous range of
+ * every level's candidate list).  Per sweep, on every rank:
+ *     uwt_shard_accumulate(t, d_sums);          // this rank's 32 fp64 partial sums
+ *     <sum d_sums over all ranks, e.g. ncclAllReduce(.., ncclDouble, ncclSum) on uwt_stream(t)>
+ *     uwt_shard_update(t, d_sums, &done);       // break test, solve, update -- identical
+ *                                               // on every rank, no broadcast needed
+ * until done != 0, then uwt_shard_result.  d_sums32: 32 doubles in DEVICE memory owned by the
+ * caller (layout: 21 upper-triangular J^T J terms, 6 J^T r terms, sum r^2, N_valid, 3 pad). */
+int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int nranks,
+                    const float* init_pose7);
+int uwt_shard_accumulate(uwt_tracker* t, double* d_sums32);
+int uwt_shard_update(uwt_tracker* t, const double* d_sums32, int* done);
+int uwt_shard_result(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats);
 /* Tracker::WarpFunction on host points (n x 4 floats [x y Z W]) at a pyramid level. */
 int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,
                     float* out4);

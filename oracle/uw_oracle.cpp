@@ -430,6 +430,156 @@ void uwo_build_pyramid(const uwo_params* p, uint8_t* const* images) {
     uwo_pyr_down(images[l - 1], p->width >> (l - 1), p->height >> (l - 1), images[l]);
 }
 
+// One residual sweep (Tracker.cpp:422-490 + the sums of :559-562) over candidate rows
+// [lo, hi) of one level at pose7.  sums32: 21 upper-triangular J^T J terms, 6 J^T (50 r)
+// terms (b is minus these), sum r^2, N_valid, 3 x 0.  The structure is the reference's: a
+// separate WarpFunction pass, then materialised Jacobian / residual arrays, then the products.
+int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8_t* I2,
+                    const int16_t* gx, const int16_t* gy, const float* cand, int lo, int hi,
+                    const float* pose7, double* sums32) {
+  int wl[UWO_MAX_LEVELS], hl[UWO_MAX_LEVELS];
+  float fxl[UWO_MAX_LEVELS], fyl[UWO_MAX_LEVELS], cxl[UWO_MAX_LEVELS], cyl[UWO_MAX_LEVELS],
+      ifx[UWO_MAX_LEVELS], ify[UWO_MAX_LEVELS];
+  if (p->levels > UWO_MAX_LEVELS || lvl < 0 || lvl >= p->levels || lo < 0 || hi < lo) return -1;
+  uwo_init_pyramid(p->width, p->height, p->fx, p->fy, p->cx, p->cy, p->levels, wl, hl, fxl, fyl,
+                   cxl, cyl, ifx, ify);
+  const int n = hi - lo;
+  const float* pts = cand + (size_t)lo * 4;
+  const int cols = wl[lvl], rows = hl[lvl];
+  const float fx = fxl[lvl], fy = fyl[lvl];
+  const int threads = p->threads < 1 ? 1 : p->threads;
+  std::vector<float> warped((size_t)n * 4), J((size_t)n * 6), r50(n);
+  std::vector<unsigned char> valid(n);
+  // --- WarpFunction (separate pass over all points, Tracker.cpp:422) ---
+  parallel_chunks(threads, [&](int c) {
+    const int a = (int)((long long)n * c / threads), b = (int)((long long)n * (c + 1) / threads);
+    uwo_warp(pts + (size_t)a * 4, b - a, pose7, fx, fy, cxl[lvl], cyl[lvl], ifx[lvl], ify[lvl],
+             warped.data() + (size_t)a * 4);
+  });
+  // --- residuals and Jacobian rows (Tracker.cpp:432-490) ---
+  std::vector<long long> part_r2(threads, 0);
+  std::vector<int> part_nv(threads, 0);
+  parallel_chunks(threads, [&](int c) {
+    const int a = (int)((long long)n * c / threads), b = (int)((long long)n * (c + 1) / threads);
+    long long sum_r2 = 0;
+    int n_valid = 0;
+    for (int i = a; i < b; ++i) {
+      const float x1 = pts[(size_t)i * 4 + 0], y1 = pts[(size_t)i * 4 + 1];
+      const float x2 = warped[(size_t)i * 4 + 0], y2 = warped[(size_t)i * 4 + 1],
+                  z2 = warped[(size_t)i * 4 + 2];
+      valid[i] = 0;
+      if (y2 > 0 && y2 < rows && x2 > 0 && x2 < cols && z2 != 0) {  // Tracker.cpp:450-451
+        float inv_z2 = 1 / z2;                                      // Tracker.cpp:447
+        if (inv_z2 < 0) inv_z2 = 0;                                 // Tracker.cpp:452-453
+        float Jw0[6], Jw1[6];                                       // Tracker.cpp:455-467
+        Jw0[0] = fx * inv_z2;
+        Jw0[1] = 0.0f;
+        Jw0[2] = -(fx * x2 * inv_z2 * inv_z2);
+        Jw0[3] = -(fx * x2 * y2 * inv_z2 * inv_z2);
+        Jw0[4] = (fx * (1 + x2 * x2 * inv_z2 * inv_z2));
+        Jw0[5] = -fx * y2 * inv_z2;
+        Jw1[0] = 0.0f;
+        Jw1[1] = fy * inv_z2;
+        Jw1[2] = -(fy * y2 * inv_z2 * inv_z2);
+        Jw1[3] = -(fy * (1 + y2 * y2 * inv_z2 * inv_z2));
+        Jw1[4] = fy * x2 * y2 * inv_z2 * inv_z2;
+        Jw1[5] = fy * x2 * inv_z2;
+        // nearest sample at round-half-away, clamped to the image (U1)
+        int xi = iround_half_away(x2), yi = iround_half_away(y2);
+        if (xi > cols - 1) xi = cols - 1;
+        if (yi > rows - 1) yi = rows - 1;
+        const int i1 = I1[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:471
+        const int i2 = I2[(size_t)yi * cols + xi];            // Tracker.cpp:472
+        const int r = i2 - i1;                                // Tracker.cpp:474
+        const float jlx = gx[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:476
+        const float jly = gy[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:477
+        // Jl * Jw (Tracker.cpp:479) is cv::gemm: double accumulators, one rounding
+        for (int q = 0; q < 6; ++q)
+          J[(size_t)i * 6 + q] =
+              (float)((double)jlx * (double)Jw0[q] + (double)jly * (double)Jw1[q]);
+        r50[i] = (float)r * p->residual_scale;  // Tracker.cpp:559 (exact)
+        valid[i] = 1;
+        sum_r2 += (long long)r * r;
+        ++n_valid;
+      }
+    }
+    part_r2[c] = sum_r2;
+    part_nv[c] = n_valid;
+  });
+  long long sum_r2 = 0;
+  int n_valid = 0;
+  for (int c = 0; c < threads; ++c) {
+    sum_r2 += part_r2[c];
+    n_valid += part_nv[c];
+  }
+  for (int i = 0; i < 32; ++i) sums32[i] = 0.0;
+  // Tracker.cpp:559-562: A = J^T J, b = -J^T (50 r)
+  if (p->accum_mode == UWO_ACCUM_LONGDOUBLE)
+    accumulate<long double>(J.data(), r50.data(), valid.data(), n, threads, sums32, sums32 + 21);
+  else
+    accumulate<double>(J.data(), r50.data(), valid.data(), n, threads, sums32, sums32 + 21);
+  sums32[27] = (double)sum_r2;
+  sums32[28] = (double)n_valid;
+  return 0;
+}
+
+// Tracker.cpp:495-574 on the (reduced) sums of one sweep: break test, solve, pose update.
+// pose7 / last_error are updated in place.  Returns 1 when the level is finished, else 0.
+int uwo_gn_update(const uwo_params* p, const double* sums32, int k, float* pose7,
+                  float* last_error, uwo_iter_trace* tr) {
+  const long long sum_r2 = (long long)sums32[27];
+  const int n_valid = (int)sums32[28];
+  if (tr) {
+    tr->n_valid = n_valid;
+    tr->sum_r2 = sum_r2;
+  }
+  if (n_valid == 0) {  // U2: nothing to optimise on this level
+    if (tr) tr->broke = 1;
+    return 1;
+  }
+  // Tracker.cpp:499-502: error = (1/N) r^T r  (U3)
+  const float inv_num = 1.0 / n_valid;
+  const float error = (float)((double)inv_num * (double)sum_r2);
+  if (tr) tr->error = error;
+  // Tracker.cpp:508: break test (the update that led here is kept)
+  if (error >= *last_error || k == p->max_iterations - 1 ||
+      std::fabs(error - *last_error) < p->epsilon) {
+    if (tr) tr->broke = 1;
+    return 1;
+  }
+  *last_error = error;  // Tracker.cpp:529
+  float A[36], b[6], delta[6];
+  {
+    int idx = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int c = a; c < 6; ++c) {
+        A[a * 6 + c] = A[c * 6 + a] = (float)sums32[idx];
+        ++idx;
+      }
+    for (int a = 0; a < 6; ++a) b[a] = (float)(-sums32[21 + a]);
+  }
+  // Tracker.cpp:564: deltaMat = A.inv() * b
+  if (p->solve_mode == UWO_SOLVE_LU) {
+    uwo_lu_solve6(A, b, delta);
+  } else {
+    float Ainv[36];
+    uwo_lu_invert6(A, Ainv);
+    for (int a = 0; a < 6; ++a) {
+      double s = 0.0;
+      for (int c = 0; c < 6; ++c) s += (double)Ainv[a * 6 + c] * (double)b[c];
+      delta[a] = (float)s;
+    }
+  }
+  // Tracker.cpp:574: current_pose = current_pose * SE3::exp(delta)
+  pose_to7(se3_mul(pose_from7(pose7), se3_exp(delta)), pose7);
+  if (tr) {
+    std::memcpy(tr->A, A, sizeof(A));
+    std::memcpy(tr->b, b, sizeof(b));
+    std::memcpy(tr->delta, delta, sizeof(delta));
+  }
+  return 0;
+}
+
 int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
                       const uint8_t* const* cur_images, const int16_t* const* gxs,
                       const int16_t* const* gys, const float* const* cand, const int* ncand,
@@ -437,189 +587,48 @@ int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
                       uwo_iter_trace* trace, int trace_cap, int* n_trace) {
   const int L = p->levels;
   if (L > UWO_MAX_LEVELS || p->first_level >= L || p->last_level < 0) return -1;
-  int wl[UWO_MAX_LEVELS], hl[UWO_MAX_LEVELS];
-  float fxl[UWO_MAX_LEVELS], fyl[UWO_MAX_LEVELS], cxl[UWO_MAX_LEVELS], cyl[UWO_MAX_LEVELS],
-      ifx[UWO_MAX_LEVELS], ify[UWO_MAX_LEVELS];
-  uwo_init_pyramid(p->width, p->height, p->fx, p->fy, p->cx, p->cy, L, wl, hl, fxl, fyl, cxl,
-                   cyl, ifx, ify);
   if (stats) std::memset(stats, 0, sizeof(*stats));
   int nt = 0;
-
   // Tracker.cpp:385: identity start (init_pose7 is an extension; NULL = reference)
-  Pose pose;
+  float pose7[7];
   if (init_pose7) {
-    pose = pose_from7(init_pose7);
+    std::memcpy(pose7, init_pose7, sizeof(pose7));
   } else {
     const float zero6[6] = {0, 0, 0, 0, 0, 0};
-    pose = se3_exp(zero6);
+    pose_to7(se3_exp(zero6), pose7);
   }
-
-  std::vector<float> warped, J, r50;
-  std::vector<unsigned char> valid;
-  const int threads = p->threads < 1 ? 1 : p->threads;
-
   for (int lvl = p->first_level; lvl >= p->last_level; --lvl) {  // Tracker.cpp:389
     float last_error = 50000.0f;                                  // Tracker.cpp:393
-    const int n = ncand[lvl];
-    const float* pts = cand[lvl];
-    const uint8_t* I1 = prev_images[lvl];
-    const uint8_t* I2 = cur_images[lvl];
-    const int16_t* gx = gxs[lvl];
-    const int16_t* gy = gys[lvl];
-    const int cols = wl[lvl], rows = hl[lvl];
-    const float fx = fxl[lvl], fy = fyl[lvl];
-    warped.resize((size_t)n * 4);
-    J.resize((size_t)n * 6);
-    r50.resize(n);
-    valid.resize(n);
-    if (stats) stats->n_points[lvl] = n;
-
+    if (stats) stats->n_points[lvl] = ncand[lvl];
     for (int k = 0; k < p->max_iterations; ++k) {  // Tracker.cpp:414
-      float pose7[7];
-      pose_to7(pose, pose7);
-      // --- WarpFunction (separate pass over all points, Tracker.cpp:422) ---
-      parallel_chunks(threads, [&](int c) {
-        const int lo = (int)((long long)n * c / threads),
-                  hi = (int)((long long)n * (c + 1) / threads);
-        uwo_warp(pts + (size_t)lo * 4, hi - lo, pose7, fx, fy, cxl[lvl], cyl[lvl], ifx[lvl],
-                 ify[lvl], warped.data() + (size_t)lo * 4);
-      });
-      // --- residuals and Jacobian rows (Tracker.cpp:432-490) ---
-      std::vector<long long> part_r2(threads, 0);
-      std::vector<int> part_nv(threads, 0);
-      parallel_chunks(threads, [&](int c) {
-      const int lo = (int)((long long)n * c / threads),
-                hi = (int)((long long)n * (c + 1) / threads);
-      long long sum_r2 = 0;
-      int n_valid = 0;
-      for (int i = lo; i < hi; ++i) {
-        const float x1 = pts[(size_t)i * 4 + 0], y1 = pts[(size_t)i * 4 + 1];
-        const float x2 = warped[(size_t)i * 4 + 0], y2 = warped[(size_t)i * 4 + 1],
-                    z2 = warped[(size_t)i * 4 + 2];
-        valid[i] = 0;
-        if (y2 > 0 && y2 < rows && x2 > 0 && x2 < cols && z2 != 0) {  // Tracker.cpp:450-451
-          float inv_z2 = 1 / z2;                                      // Tracker.cpp:447
-          if (inv_z2 < 0) inv_z2 = 0;                                 // Tracker.cpp:452-453
-          float Jw0[6], Jw1[6];                                       // Tracker.cpp:455-467
-          Jw0[0] = fx * inv_z2;
-          Jw0[1] = 0.0f;
-          Jw0[2] = -(fx * x2 * inv_z2 * inv_z2);
-          Jw0[3] = -(fx * x2 * y2 * inv_z2 * inv_z2);
-          Jw0[4] = (fx * (1 + x2 * x2 * inv_z2 * inv_z2));
-          Jw0[5] = -fx * y2 * inv_z2;
-          Jw1[0] = 0.0f;
-          Jw1[1] = fy * inv_z2;
-          Jw1[2] = -(fy * y2 * inv_z2 * inv_z2);
-          Jw1[3] = -(fy * (1 + y2 * y2 * inv_z2 * inv_z2));
-          Jw1[4] = fy * x2 * y2 * inv_z2 * inv_z2;
-          Jw1[5] = fy * x2 * inv_z2;
-          // nearest sample at round-half-away, clamped to the image (U1)
-          int xi = iround_half_away(x2), yi = iround_half_away(y2);
-          if (xi > cols - 1) xi = cols - 1;
-          if (yi > rows - 1) yi = rows - 1;
-          const int i1 = I1[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:471
-          const int i2 = I2[(size_t)yi * cols + xi];            // Tracker.cpp:472
-          const int r = i2 - i1;                                // Tracker.cpp:474
-          const float jlx = gx[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:476
-          const float jly = gy[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:477
-          // Jl * Jw (Tracker.cpp:479) is cv::gemm: double accumulators, one rounding
-          for (int c = 0; c < 6; ++c)
-            J[(size_t)i * 6 + c] =
-                (float)((double)jlx * (double)Jw0[c] + (double)jly * (double)Jw1[c]);
-          r50[i] = (float)r * p->residual_scale;  // Tracker.cpp:559 (exact)
-          valid[i] = 1;
-          sum_r2 += (long long)r * r;
-          ++n_valid;
-        }
-      }
-      part_r2[c] = sum_r2;
-      part_nv[c] = n_valid;
-      });
-      long long sum_r2 = 0;
-      int n_valid = 0;
-      for (int c = 0; c < threads; ++c) {
-        sum_r2 += part_r2[c];
-        n_valid += part_nv[c];
-      }
+      double sums[32];
+      int rc = uwo_sweep_range(p, lvl, prev_images[lvl], cur_images[lvl], gxs[lvl], gys[lvl],
+                               cand[lvl], 0, ncand[lvl], pose7, sums);
+      if (rc) return rc;
       if (stats) stats->evaluations[lvl] = k + 1;
       uwo_iter_trace* tr = (trace && nt < trace_cap) ? &trace[nt] : nullptr;
       if (tr) {
         std::memset(tr, 0, sizeof(*tr));
         tr->level = lvl;
         tr->k = k;
-        tr->n_valid = n_valid;
-        tr->sum_r2 = sum_r2;
       }
-      if (n_valid == 0) {  // U2: nothing to optimise on this level
-        if (tr) {
-          tr->broke = 1;
-          pose_to7(pose, tr->pose);
-          ++nt;
-        }
-        break;
-      }
-      // Tracker.cpp:499-502: error = (1/N) r^T r  (U3)
-      const float inv_num = 1.0 / n_valid;
-      const float error = (float)((double)inv_num * (double)sum_r2);
-      if (tr) tr->error = error;
-      // Tracker.cpp:508: break test (the update that led here is kept)
-      if (error >= last_error || k == p->max_iterations - 1 ||
-          std::fabs(error - last_error) < p->epsilon) {
-        if (stats) stats->final_error[lvl] = error;
-        if (tr) {
-          tr->broke = 1;
-          pose_to7(pose, tr->pose);
-          ++nt;
-        }
-        break;
-      }
-      last_error = error;  // Tracker.cpp:529
-      if (stats) {
-        stats->final_error[lvl] = error;
-        stats->iterations[lvl] = k + 1;
-      }
-
-      // Tracker.cpp:559-562: A = J^T J, b = -J^T (50 r)
-      double A21[21], b6d[6];
-      if (p->accum_mode == UWO_ACCUM_LONGDOUBLE)
-        accumulate<long double>(J.data(), r50.data(), valid.data(), n, threads, A21, b6d);
-      else
-        accumulate<double>(J.data(), r50.data(), valid.data(), n, threads, A21, b6d);
-      float A[36], b[6], delta[6];
-      {
-        int idx = 0;
-        for (int a = 0; a < 6; ++a)
-          for (int c = a; c < 6; ++c) {
-            A[a * 6 + c] = A[c * 6 + a] = (float)A21[idx];
-            ++idx;
-          }
-        for (int a = 0; a < 6; ++a) b[a] = (float)(-b6d[a]);
-      }
-      // Tracker.cpp:564: deltaMat = A.inv() * b
-      if (p->solve_mode == UWO_SOLVE_LU) {
-        uwo_lu_solve6(A, b, delta);
-      } else {
-        float Ainv[36];
-        uwo_lu_invert6(A, Ainv);
-        for (int a = 0; a < 6; ++a) {
-          double s = 0.0;
-          for (int c = 0; c < 6; ++c) s += (double)Ainv[a * 6 + c] * (double)b[c];
-          delta[a] = (float)s;
-        }
-      }
-      // Tracker.cpp:574: current_pose = current_pose * SE3::exp(delta)
-      pose = se3_mul(pose, se3_exp(delta));
+      const float err_before = last_error;
+      const int brk = uwo_gn_update(p, sums, k, pose7, &last_error, tr);
       if (tr) {
-        std::memcpy(tr->A, A, sizeof(A));
-        std::memcpy(tr->b, b, sizeof(b));
-        std::memcpy(tr->delta, delta, sizeof(delta));
-        pose_to7(pose, tr->pose);
+        std::memcpy(tr->pose, pose7, sizeof(pose7));
         ++nt;
       }
+      if (stats && sums[28] > 0) {
+        const float inv_num = 1.0 / (int)sums[28];
+        stats->final_error[lvl] = (float)((double)inv_num * (double)(long long)sums[27]);
+        if (!brk) stats->iterations[lvl] = k + 1;
+      }
+      (void)err_before;
+      if (brk) break;
     }
-    if (lvl != 0) pose = se3_scale_level(pose);  // Tracker.cpp:580-590
+    if (lvl != 0) pose_to7(se3_scale_level(pose_from7(pose7)), pose7);  // Tracker.cpp:580-590
   }
-  pose_to7(pose, out_pose7);  // Tracker.cpp:595
+  std::memcpy(out_pose7, pose7, sizeof(pose7));  // Tracker.cpp:595
   if (n_trace) *n_trace = nt;
   return 0;
 }

@@ -110,6 +110,15 @@ int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
                       const float* init_pose7, float* out_pose7, uwo_stats* stats,
                       uwo_iter_trace* trace, int trace_cap, int* n_trace);
 
+/* The two halves of one Gauss-Newton iteration, exposed so that the sharded (multi-rank) host
+ * protocol can be exercised on CPU: a residual sweep over candidate rows [lo,hi) -> 32 sums,
+ * and the update on (reduced) sums.  uwo_estimate_pose is built from these two. */
+int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8_t* I2,
+                    const int16_t* gx, const int16_t* gy, const float* cand, int lo, int hi,
+                    const float* pose7, double* sums32);
+int uwo_gn_update(const uwo_params* p, const double* sums32, int k, float* pose7,
+                  float* last_error, uwo_iter_trace* tr);
+
 /* Convenience for benchmarks: full track on two level-0 frames (allocates internally):
  * pyramid(prev), pyramid(cur), ApplyGradient(prev), ObtainCandidatePoints(prev),
  * EstimatePose(prev,cur).  seconds[0..3] = pyramid, gradient, candidates, estimate. */

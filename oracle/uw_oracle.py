@@ -294,3 +294,39 @@ def track_sequence(params, frames):
     if rc != 0:
         raise RuntimeError("uwo_track_sequence failed: %d" % rc)
     return poses, secs, list(stats)
+
+
+def sweep_range(params, frame_prev, frame_cur, lvl, lo, hi, pose7):
+    """uwo_sweep_range on FrameData: the 32 sums of candidate rows [lo, hi) of level lvl."""
+    L = lib()
+    u8p, i16p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_float)
+    L.uwo_sweep_range.restype = C.c_int
+    L.uwo_sweep_range.argtypes = [C.POINTER(Params), C.c_int, u8p, u8p, i16p, i16p, f32p, C.c_int,
+                                  C.c_int, f32p, C.POINTER(C.c_double)]
+    I1 = np.ascontiguousarray(frame_prev.images[lvl])
+    I2 = np.ascontiguousarray(frame_cur.images[lvl])
+    gx = np.ascontiguousarray(frame_prev.gx[lvl])
+    gy = np.ascontiguousarray(frame_prev.gy[lvl])
+    cd = np.ascontiguousarray(frame_prev.cand[lvl], np.float32)
+    pose = np.ascontiguousarray(pose7, np.float32)
+    sums = np.zeros(32, np.float64)
+    rc = L.uwo_sweep_range(C.byref(params), lvl, _p(I1, C.c_uint8), _p(I2, C.c_uint8),
+                           _p(gx, C.c_int16), _p(gy, C.c_int16), _p(cd, C.c_float), lo, hi,
+                           _p(pose, C.c_float), _p(sums, C.c_double))
+    if rc != 0:
+        raise RuntimeError("uwo_sweep_range failed: %d" % rc)
+    return sums
+
+
+def gn_update(params, sums32, k, pose7, last_error):
+    """uwo_gn_update: returns (level_finished, new_pose7, new_last_error)."""
+    L = lib()
+    L.uwo_gn_update.restype = C.c_int
+    L.uwo_gn_update.argtypes = [C.POINTER(Params), C.POINTER(C.c_double), C.c_int,
+                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
+    sums = np.ascontiguousarray(sums32, np.float64)
+    pose = np.array(pose7, np.float32)
+    le = C.c_float(last_error)
+    brk = L.uwo_gn_update(C.byref(params), _p(sums, C.c_double), k, _p(pose, C.c_float),
+                          C.byref(le), None)
+    return bool(brk), pose, le.value

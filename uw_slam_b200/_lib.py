@@ -66,6 +66,10 @@ SIGNATURES = {
     "uwt_estimate_pose": (C.c_int, [_H, C.c_int, _ip, _ip, _fp, _fp, C.POINTER(TrackStats)]),
     "uwt_estimate_pose_async": (C.c_int, [_H, C.c_int, _ip, _ip, _fp]),
     "uwt_fetch_poses": (C.c_int, [_H, C.c_int, _fp, C.POINTER(TrackStats)]),
+    "uwt_shard_begin": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "uwt_shard_accumulate": (C.c_int, [_H, C.c_void_p]),
+    "uwt_shard_update": (C.c_int, [_H, C.c_void_p, _ip]),
+    "uwt_shard_result": (C.c_int, [_H, _fp, C.POINTER(TrackStats)]),
     "uwt_warp_points": (C.c_int, [_H, _fp, C.c_int, _fp, C.c_int, _fp]),
     "uwt_get_image": (C.c_int, [_H, C.c_int, C.c_int, _u8p]),
     "uwt_get_gradients": (C.c_int, [_H, C.c_int, C.c_int, _i16p, _i16p, _u8p]),

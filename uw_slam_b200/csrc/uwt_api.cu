@@ -56,6 +56,12 @@ struct uwt_tracker {
   int stage_next = 0;
   size_t stage_frames = 0;
   cudaEvent_t poses_ready = nullptr;  // recorded after the D2H of the last estimate
+  // sharded single-frame mode
+  ShardState* d_shard = nullptr;
+  double* d_shard_partials = nullptr;
+  int* d_shard_done = nullptr;
+  int* h_shard_done = nullptr;  // pinned
+  bool shard_active = false;
   float* d_out_poses = nullptr;
   uwt_track_stats* d_stats = nullptr;
   float* h_out_poses = nullptr;       // pinned
@@ -248,6 +254,10 @@ void destroy_impl(uwt_tracker* t) {
     if (t->stage_free[i]) cudaEventDestroy(t->stage_free[i]);
   }
   if (t->poses_ready) cudaEventDestroy(t->poses_ready);
+  cudaFree(t->d_shard);
+  cudaFree(t->d_shard_partials);
+  cudaFree(t->d_shard_done);
+  if (t->h_shard_done) cudaFreeHost(t->h_shard_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   cudaFree(t->d_out_poses);
   cudaFree(t->d_stats);
@@ -375,6 +385,10 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
     CREATE_CUDA(cudaEventCreateWithFlags(&t->stage_free[i], cudaEventDisableTiming));
   }
   CREATE_CUDA(cudaEventCreateWithFlags(&t->poses_ready, cudaEventDisableTiming));
+  CREATE_CUDA(cudaMalloc(&t->d_shard, sizeof(ShardState)));
+  CREATE_CUDA(cudaMalloc(&t->d_shard_partials, sizeof(double) * 32 * kShardMaxGrid));
+  CREATE_CUDA(cudaMalloc(&t->d_shard_done, sizeof(int)));
+  CREATE_CUDA(cudaHostAlloc(&t->h_shard_done, sizeof(int), cudaHostAllocDefault));
   CREATE_CUDA(cudaMalloc(&t->d_out_poses, sizeof(float) * 7 * F));
   CREATE_CUDA(cudaMalloc(&t->d_stats, sizeof(uwt_track_stats) * F));
   CREATE_CUDA(cudaHostAlloc(&t->h_out_poses, sizeof(float) * 7 * F, cudaHostAllocDefault));
@@ -659,6 +673,79 @@ int uwt_estimate_pose(uwt_tracker* t, int n, const int* prev_slots, const int* c
   int rc = uwt_estimate_pose_async(t, n, prev_slots, cur_slots, init_poses7);
   if (rc) return rc;
   return uwt_fetch_poses(t, n, out_poses7, stats);
+}
+
+int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int nranks,
+                    const float* init_pose7) {
+  int rc = check_slots(t, 1, &prev_slot);
+  if (rc) return rc;
+  if ((rc = check_slots(t, 1, &cur_slot))) return rc;
+  if (nranks < 1 || rank < 0 || rank >= nranks)
+    return fail(t, UWT_E_INVALID, "bad shard rank %d of %d", rank, nranks);
+  if (!t->slots[prev_slot].candidates)
+    return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slot);
+  if (!t->slots[cur_slot].pyramid) return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slot);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  ShardState s;
+  std::memset(&s, 0, sizeof(s));
+  // SE3::exp(0) is exactly the identity (Tracker.cpp:385)
+  const float ident[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
+  std::memcpy(s.pose, init_pose7 ? init_pose7 : ident, sizeof(ident));
+  s.last_error = 50000.0f;
+  s.level = t->cfg.first_level;
+  s.rank = rank;
+  s.nranks = nranks;
+  s.prev_slot = prev_slot;
+  s.cur_slot = cur_slot;
+  UWT_CUDA(t, cudaMemcpyAsync(t->d_shard, &s, sizeof(s), cudaMemcpyHostToDevice, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));  // `s` is a stack object
+  t->shard_active = true;
+  return UWT_OK;
+}
+
+int uwt_shard_accumulate(uwt_tracker* t, double* d_sums32) {
+  if (!t) return UWT_E_INVALID;
+  if (!t->shard_active) return fail(t, UWT_E_STATE, "call uwt_shard_begin first");
+  if (!d_sums32) return fail(t, UWT_E_INVALID, "d_sums32 is NULL");
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  ProfSpan span(t, UWT_K_ESTIMATE);
+  const int k = launch_shard_accumulate(t->geom, t->pools, t->d_shard, t->d_shard_partials,
+                                        d_sums32, kShardMaxGrid, t->stream);
+  if (k < 0) return fail(t, UWT_E_CUDA, "shard accumulate launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  span.done(k);
+  return UWT_OK;
+}
+
+int uwt_shard_update(uwt_tracker* t, const double* d_sums32, int* done) {
+  if (!t) return UWT_E_INVALID;
+  if (!t->shard_active) return fail(t, UWT_E_STATE, "call uwt_shard_begin first");
+  if (!d_sums32 || !done) return fail(t, UWT_E_INVALID, "NULL argument");
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  const int k = launch_shard_update(t->geom, t->pools, t->d_shard, d_sums32, t->d_shard_done,
+                                    t->stream);
+  if (k < 0) return fail(t, UWT_E_CUDA, "shard update launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  UWT_CUDA(t, cudaMemcpyAsync(t->h_shard_done, t->d_shard_done, sizeof(int),
+                              cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  *done = *t->h_shard_done;
+  return UWT_OK;
+}
+
+int uwt_shard_result(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats) {
+  if (!t) return UWT_E_INVALID;
+  if (!t->shard_active) return fail(t, UWT_E_STATE, "call uwt_shard_begin first");
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  ShardState s;
+  UWT_CUDA(t, cudaMemcpyAsync(&s, t->d_shard, sizeof(s), cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  if (!s.done) return fail(t, UWT_E_STATE, "sharded estimate has not finished");
+  if (out_pose7) std::memcpy(out_pose7, s.pose, sizeof(s.pose));
+  if (stats) *stats = s.stats;
+  return UWT_OK;
 }
 
 int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,

@@ -77,6 +77,17 @@ struct EstimateIO {
   int trace_cap;
 };
 
+// Device-resident state of the sharded single-frame mode (one problem split over ranks).
+struct ShardState {
+  float pose[7];
+  float last_error;
+  int level, k, done;
+  int rank, nranks, prev_slot, cur_slot;
+  unsigned ticket;
+  uwt_track_stats stats;
+};
+constexpr int kShardMaxGrid = 148 * 2;
+
 // kernel launchers (each returns the number of kernels launched, or <0 on launch error)
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
                    size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st);
@@ -84,6 +95,10 @@ int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cu
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
 int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
                     cudaStream_t st);
+int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, double* partials,
+                            double* out32, int grid, cudaStream_t stream);
+int launch_shard_update(const Geom& g, const Pools& p, ShardState* st, const double* sums32,
+                        int* done_out, cudaStream_t stream);
 int launch_warp_points(const Geom& g, const float* d_pts4, int n, const float* d_pose7, int level,
                        float* d_out4, cudaStream_t st);
 

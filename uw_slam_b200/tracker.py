@@ -227,6 +227,28 @@ class Tracker:
                                               out.ctypes.data_as(L._fp)))
         return out
 
+    # -- sharded single-frame mode (uwt_shard_*) -------------------------------------------
+    def ShardBegin(self, prev_slot, cur_slot, rank, nranks, init_pose=None):
+        ip = None
+        if init_pose is not None:
+            self._ip = np.ascontiguousarray(init_pose, np.float32)
+            ip = self._ip.ctypes.data_as(L._fp)
+        self._check(self._lib.uwt_shard_begin(self._h, prev_slot, cur_slot, rank, nranks, ip))
+
+    def ShardAccumulate(self, dev_sums_ptr):
+        self._check(self._lib.uwt_shard_accumulate(self._h, dev_sums_ptr))
+
+    def ShardUpdate(self, dev_sums_ptr):
+        done = C.c_int(0)
+        self._check(self._lib.uwt_shard_update(self._h, dev_sums_ptr, C.byref(done)))
+        return bool(done.value)
+
+    def ShardResult(self):
+        out = np.empty(7, np.float32)
+        st = L.TrackStats()
+        self._check(self._lib.uwt_shard_result(self._h, out.ctypes.data_as(L._fp), C.byref(st)))
+        return out, st
+
     def synchronize(self):
         self._check(self._lib.uwt_synchronize(self._h))
 
