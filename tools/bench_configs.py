@@ -1,0 +1,218 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs 1, 3, 4); bench.py is config 2, the headline.
+
+  --workload euroc_seq   config 1: 752x480 EuRoC-calibration sequence, ONE stream, frame-to-
+                         keyframe (re-keyed every 8 frames): single-problem latency
+  --workload batch8192   config 3: 8192 independent 640x480 pairs, block-partitioned over the
+                         ranks (strong scaling, no comms), processed in resident chunks
+  --workload shard4k     config 4: one 3840x2160 pair, GN loop sharded over the ranks with one
+                         NCCL all-reduce of the 32 normal-equation sums per sweep
+
+Launch like bench.py (python tools/bench_configs.py ... or torchrun for N > 1).  One JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from uw_slam_b200 import synth  # noqa: E402
+
+
+def env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def make_tracker(calib, device, **cfg):
+    import uw_slam_b200 as U
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        device=device, **cfg)
+    return t
+
+
+def euroc_seq(args, torch, dist, rank, local_rank, world):
+    calib, n_frames, rekey = "euroc", 64, 8
+    w, h = synth.CALIB[calib][:2]
+    frames, _, _ = synth.render_sequence(calib, 11, n_frames, rot=1.5e-3, trans=1.5e-3)
+    host = torch.from_numpy(np.stack(frames)).pin_memory()
+    t = make_tracker(calib, local_rank, max_frames=2)
+    KEY, CUR = 0, 1
+
+    def run(collect):
+        poses, sweeps = [], 0
+        t.AddFramesHostPtr([KEY], host[0].data_ptr(), w, w * h)
+        t.ApplyGradient([KEY])
+        t.ObtainCandidatePoints([KEY])
+        for i in range(1, n_frames):
+            t.AddFramesHostPtr([CUR], host[i].data_ptr(), w, w * h)
+            pose, st = t.EstimatePose([KEY], [CUR], return_stats=True)   # keyframe -> frame i
+            if collect:
+                poses.append(pose[0])
+                sweeps += sum(st[0].evaluations)
+            if i % rekey == 0:  # the current frame becomes the keyframe
+                t.AddFramesHostPtr([KEY], host[i].data_ptr(), w, w * h)
+                t.ApplyGradient([KEY])
+                t.ObtainCandidatePoints([KEY])
+        return poses, sweeps
+
+    run(False)
+    t.synchronize()
+    t.profile(True)
+    t0 = time.perf_counter()
+    poses, sweeps = run(True)
+    t.synchronize()
+    dt = time.perf_counter() - t0
+    prof = t.profile_read()
+    # CPU oracle on the same sequence (bounded: it is only 63 tracks)
+    from oracle import uw_oracle as O
+    p = O.default_params(*synth.CALIB[calib], accum_mode=0)
+    t1 = time.perf_counter()
+    key = O.FrameData(frames[0])
+    same = True
+    for i in range(1, n_frames):
+        cur = O.FrameData(frames[i], with_candidates=False)
+        op, _, _ = O.estimate_pose(p, key, cur)
+        same &= bool(np.array_equal(op, poses[i - 1]))
+        if i % rekey == 0:
+            key = O.FrameData(frames[i])
+    cpu_dt = time.perf_counter() - t1
+    est_ms, est_l = prof["estimate"]
+    return {"metric": "pose-tracks/sec, single stream 752x480 (frame-to-keyframe)",
+            "value": (n_frames - 1) / dt, "unit": "tracks/s", "tracks": n_frames - 1,
+            "ms_per_track_e2e": 1e3 * dt / (n_frames - 1),
+            "estimate_kernel_us_per_track": 1e3 * est_ms / max(est_l, 1),
+            "us_per_gn_sweep": 1e3 * est_ms / max(sweeps, 1), "sweeps_per_track":
+            sweeps / (n_frames - 1),
+            "cpu_oracle_tracks_per_s": (n_frames - 1) / cpu_dt,
+            "poses_bit_identical_to_oracle": same, "n_gpus": 1}
+
+
+def batch8192(args, torch, dist, rank, local_rank, world):
+    calib, total = "tum", args.pairs
+    w, h = synth.CALIB[calib][:2]
+    dev = torch.device("cuda", local_rank)
+    lo, hi = total * rank // world, total * (rank + 1) // world   # pair i -> GPU floor(i*G/B)
+    mine = hi - lo
+    chunk = min(args.chunk, mine)
+    t = make_tracker(calib, local_rank, max_frames=2 * chunk)
+    # resident inputs: all of this rank's pairs, rendered on the device
+    prev = torch.empty((mine, h, w), dtype=torch.uint8, device=dev)
+    cur = torch.empty_like(prev)
+    for a in range(0, mine, 256):
+        b = min(a + 256, mine)
+        p_, c_ = synth.render_batch_torch(calib, list(range(lo + a, lo + b)), dev)
+        prev[a:b], cur[a:b] = p_, c_
+    ps, cs = list(range(chunk)), list(range(chunk, 2 * chunk))
+    out = np.empty((mine, 7), np.float32)
+
+    def run():
+        for a in range(0, mine, chunk):
+            n = min(chunk, mine - a)
+            t.AddFramesDevice(ps[:n], prev[a].data_ptr())
+            t.AddFramesDevice(cs[:n], cur[a].data_ptr())
+            t.ApplyGradient(ps[:n])
+            t.ObtainCandidatePoints(ps[:n])
+            out[a:a + n] = t.EstimatePose(ps[:n], cs[:n])
+
+    run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    run()
+    t.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    res = {"metric": "pose-tracks/sec, 8192 independent 640x480 pairs (pyramids x2, gradient, "
+                     "candidates, estimate per pair; inputs resident in HBM)",
+           "value": total / float(dt.item()), "unit": "tracks/s", "pairs": total,
+           "n_gpus": world, "scaling": "strong", "chunk": chunk}
+    if rank == 0:
+        # spot-check 4 pairs against the oracle
+        from oracle import uw_oracle as O
+        p = O.default_params(*synth.CALIB[calib])
+        same = True
+        for i in [0, 1, mine // 2, mine - 1]:
+            a, b = prev[i].cpu().numpy(), cur[i].cpu().numpy()
+            op, _, _ = O.estimate_pose(p, O.FrameData(a), O.FrameData(b, with_candidates=False))
+            same &= bool(np.array_equal(op, out[i]))
+        res["spot_check_bit_identical_to_oracle"] = same
+    return res
+
+
+def shard4k(args, torch, dist, rank, local_rank, world):
+    from uw_slam_b200.sharded import TrackerShardBackend, estimate_pose_sharded
+    calib = "uhd"
+    prev, cur, _, _ = synth.render_pair(calib, 21)
+    t = make_tracker(calib, local_rank, max_frames=2)
+    t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.ApplyGradient([0])
+    t.ObtainCandidatePoints([0])
+    backend = TrackerShardBackend(t, 0, 1)
+    pose, stats, sweeps = estimate_pose_sharded(backend)
+    t.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = args.reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pose, stats, sweeps = estimate_pose_sharded(backend)
+    t.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    # the unsharded single-kernel path on the same pair (rank 0's GPU), for comparison
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        ref = t.EstimatePose([0], [1])
+    t.synchronize()
+    dt_single = (time.perf_counter() - t1) / reps
+    res = {"metric": "GN pose estimate of one 3840x2160 pair, candidate list sharded over ranks",
+           "n_gpus": world, "ms_per_estimate_sharded": 1e3 * dt, "sweeps": sweeps,
+           "us_per_sweep_sharded": 1e6 * dt / sweeps,
+           "ms_per_estimate_single_kernel_1gpu": 1e3 * dt_single,
+           "points_per_level": list(stats.n_points)[:5],
+           "pose_equals_single_gpu_kernel": bool(np.array_equal(pose, ref[0])),
+           "collective": "none" if world == 1 else "NCCL all-reduce of 32 fp64 per sweep"}
+    if rank == 0 and args.check:
+        from oracle import uw_oracle as O
+        p = O.default_params(*synth.CALIB[calib])
+        op, _, _ = O.estimate_pose(p, O.FrameData(prev), O.FrameData(cur, with_candidates=False))
+        res["pose_bit_identical_to_oracle"] = bool(np.array_equal(op, pose))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", required=True, choices=["euroc_seq", "batch8192", "shard4k"])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--pairs", type=int, default=8192)
+    ap.add_argument("--chunk", type=int, default=1024)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res = {"euroc_seq": euroc_seq, "batch8192": batch8192, "shard4k": shard4k}[args.workload](
+        args, torch, dist, rank, local_rank, world)
+    res["workload"] = args.workload
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
