@@ -120,8 +120,9 @@ int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* ho
 /* Same, from frames already resident in DEVICE memory. */
 int uwt_set_frames_device(uwt_tracker* t, int n, const int* slots, const uint8_t* dev,
                           size_t row_stride, size_t frame_stride);
-/* Tracker::ApplyGradient for n slots: gradientX_, gradientY_ (int16) and gradient_ (u8) on
- * every pyramid level. */
+/* Tracker::ApplyGradient for n slots: gradient_ (u8) on every pyramid level.  The int16
+ * gradientX_ / gradientY_ values reach the tracker through the packed candidate records; the
+ * full planes are produced on demand by uwt_get_gradients (same stencil, same integers). */
 int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots);
 /* Tracker::ObtainCandidatePoints for n slots (needs gradients): candidatePoints_ on every
  * level, in the reference's x-major order. */
@@ -164,6 +165,11 @@ int uwt_get_candidate_count(uwt_tracker* t, int slot, int level, int* n);
 /* candidatePoints_[level] as the reference stores it: rows [x, y, 1, 1] (CV_32FC1). */
 int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int capacity_rows,
                        int* n);
+/* The packed per-candidate records the Gauss-Newton kernel streams (levels first..last only),
+ * same order as uwt_get_candidates.  Bit layout of one 64-bit record:
+ *   0..11 x | 12..23 y | 24..31 I1 = images_[l](y,x) | 32..44 gradientX_[l](y,x) (13-bit two's
+ *   complement) | 45..57 gradientY_[l](y,x) | 58..63 zero. */
+int uwt_get_records(uwt_tracker* t, int slot, int level, uint64_t* packed, int capacity, int* n);
 /* Trace of problem `index` of the last uwt_estimate_pose (needs UWT_FLAG_TRACE). */
 int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, int* n);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

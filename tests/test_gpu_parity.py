@@ -61,6 +61,15 @@ def test_pyramid_gradients_candidates_bit_exact(oracle, pairs, calib):
         c = f.candidatePoints(lvl)
         assert c.shape == ref.cand[lvl].shape, ("ncand", lvl, c.shape, ref.cand[lvl].shape)
         assert np.array_equal(c, ref.cand[lvl]), ("cand", lvl)
+        if 1 <= lvl <= 4:
+            # the packed records EstimatePose streams: same order, and I1 / gradientX_ /
+            # gradientY_ at every candidate equal the reference planes
+            r = t.get_records(f.slot, lvl)
+            xs, ys = ref.cand[lvl][:, 0].astype(int), ref.cand[lvl][:, 1].astype(int)
+            assert np.array_equal(r["x"], xs) and np.array_equal(r["y"], ys)
+            assert np.array_equal(r["i1"], ref.images[lvl][ys, xs])
+            assert np.array_equal(r["gx"], ref.gx[lvl][ys, xs])
+            assert np.array_equal(r["gy"], ref.gy[lvl][ys, xs])
     t.close()
 
 

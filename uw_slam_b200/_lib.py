@@ -75,6 +75,7 @@ SIGNATURES = {
     "uwt_get_gradients": (C.c_int, [_H, C.c_int, C.c_int, _i16p, _i16p, _u8p]),
     "uwt_get_candidate_count": (C.c_int, [_H, C.c_int, C.c_int, _ip]),
     "uwt_get_candidates": (C.c_int, [_H, C.c_int, C.c_int, _fp, C.c_int, _ip]),
+    "uwt_get_records": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int, _ip]),
     "uwt_get_trace": (C.c_int, [_H, C.c_int, C.POINTER(IterTrace), C.c_int, _ip]),
     "uwt_launch_count": (C.c_longlong, [_H]),
     "uwt_profile_enable": (C.c_int, [_H, C.c_int]),

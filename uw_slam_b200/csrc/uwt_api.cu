@@ -237,7 +237,7 @@ void destroy_impl(uwt_tracker* t) {
   if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   if (t->stream) cudaStreamSynchronize(t->stream);
   Pools& p = t->pools;
-  cudaFree(p.img); cudaFree(p.gx); cudaFree(p.gy); cudaFree(p.g); cudaFree(p.gpart);
+  cudaFree(p.img); cudaFree(p.g); cudaFree(p.gpart);
   cudaFree(p.ticket); cudaFree(p.ithr); cudaFree(p.cnt); cudaFree(p.ncand);
   cudaFree(p.cand_xy); cudaFree(p.rec);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
@@ -355,8 +355,6 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   const size_t F = (size_t)c.max_frames;
   Pools& p = t->pools;
   CREATE_CUDA(cudaMalloc(&p.img, F * g.plane_elems));
-  CREATE_CUDA(cudaMalloc(&p.gx, F * g.plane_elems * sizeof(int16_t)));
-  CREATE_CUDA(cudaMalloc(&p.gy, F * g.plane_elems * sizeof(int16_t)));
   CREATE_CUDA(cudaMalloc(&p.g, F * g.plane_elems));
   CREATE_CUDA(cudaMalloc(&p.gpart, F * g.tile_elems * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.ticket, F * kMaxLevels * sizeof(uint32_t)));
@@ -800,12 +798,30 @@ int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t*
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   const LevelGeom& L = t->geom.lv[level];
   const size_t off = (size_t)slot * t->geom.plane_elems + L.plane_off;
-  if (gx)
-    UWT_CUDA(t, cudaMemcpy2DAsync(gx, L.w * 2, t->pools.gx + off, L.pitch * 2, L.w * 2, L.h,
-                                  cudaMemcpyDeviceToHost, t->stream));
-  if (gy)
-    UWT_CUDA(t, cudaMemcpy2DAsync(gy, L.w * 2, t->pools.gy + off, L.pitch * 2, L.w * 2, L.h,
-                                  cudaMemcpyDeviceToHost, t->stream));
+  if (gx || gy) {
+    // gradientX_/gradientY_ planes are not kept on the device (the tracker consumes packed
+    // records): materialise them for this slot with the same kernel and copy the level out
+    int16_t* tmp = nullptr;
+    const size_t pe = t->geom.plane_elems;
+    UWT_CUDA(t, cudaMalloc(&tmp, 2 * pe * sizeof(int16_t)));
+    ArgRegion* r;
+    if ((rc = acquire(t, &r))) { cudaFree(tmp); return rc; }
+    if ((rc = push_slots(t, r, 1, &slot, nullptr))) { cudaFree(tmp); return rc; }
+    const int k = launch_gradient(t->geom, t->pools, 1, r->d_int, t->stream, tmp, tmp + pe);
+    if (k > 0) t->launches += k;
+    release(t, r);
+    cudaError_t e = cudaSuccess;
+    if (gx)
+      e = cudaMemcpy2DAsync(gx, L.w * 2, tmp + L.plane_off, L.pitch * 2, L.w * 2, L.h,
+                            cudaMemcpyDeviceToHost, t->stream);
+    if (gy && e == cudaSuccess)
+      e = cudaMemcpy2DAsync(gy, L.w * 2, tmp + pe + L.plane_off, L.pitch * 2, L.w * 2, L.h,
+                            cudaMemcpyDeviceToHost, t->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+    cudaFree(tmp);
+    if (k < 0 || e != cudaSuccess)
+      return fail(t, UWT_E_CUDA, "gradient read-back failed: %s", cudaGetErrorString(e));
+  }
   if (g)
     UWT_CUDA(t, cudaMemcpy2DAsync(g, L.w, t->pools.g + off, L.pitch, L.w, L.h,
                                   cudaMemcpyDeviceToHost, t->stream));
@@ -849,6 +865,23 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
     pts4[i * 4 + 2] = 1.0f;
     pts4[i * 4 + 3] = 1.0f;
   }
+  return UWT_OK;
+}
+
+int uwt_get_records(uwt_tracker* t, int slot, int level, uint64_t* packed, int capacity, int* n) {
+  int cnt = 0;
+  int rc = uwt_get_candidate_count(t, slot, level, &cnt);
+  if (rc) return rc;
+  const LevelGeom& L = t->geom.lv[level];
+  if (L.rec_off < 0)
+    return fail(t, UWT_E_INVALID, "level %d is not optimised: it has no packed records", level);
+  if (n) *n = cnt;
+  if (!packed) return UWT_OK;
+  if (cnt > capacity) return fail(t, UWT_E_INVALID, "capacity %d < %d records", capacity, cnt);
+  if (cnt == 0) return UWT_OK;
+  UWT_CUDA(t, cudaMemcpyAsync(packed, t->pools.rec + (size_t)slot * t->geom.rec_elems + L.rec_off,
+                              sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
   return UWT_OK;
 }
 

@@ -15,7 +15,9 @@
 //   scatter : same tiles as count; a warp handles one column x 32 rows per step, so the
 //             selected points of a column are appended with ONE coalesced store per step
 //             (ballot + popc prefix): (x, y) -- and, on the levels EstimatePose optimises,
-//             the packed 8-byte record (x, y, I1, gx, gy) the Gauss-Newton kernel streams.
+//             the packed 8-byte record (x, y, I1, gx, gy) the Gauss-Newton kernel streams;
+//             I1 and the Scharr gx, gy of a selected pixel come from an image tile with a
+//             one-pixel halo in shared memory (no int16 gradient planes are read).
 #include "uwt_internal.cuh"
 
 namespace uwt {
@@ -41,7 +43,6 @@ __device__ __forceinline__ TileItem locate_item(const Geom& geom, int item) {
 }
 
 constexpr int kTilePitch8 = kStripW + 4;    // bytes per u8 tile row: 33 words -> no conflicts
-constexpr int kTilePitch16 = kStripW + 2;   // int16 per tile row: 65 words -> no conflicts
 
 // Loads the (kSegRows x kStripW) u8 tile at (x0, y0) row-wise into shared memory.
 __device__ __forceinline__ void load_tile_u8(const uint8_t* __restrict__ plane, const LevelGeom& L,
@@ -57,19 +58,42 @@ __device__ __forceinline__ void load_tile_u8(const uint8_t* __restrict__ plane, 
   }
 }
 
-__device__ __forceinline__ void load_tile_i16(const int16_t* __restrict__ plane, const LevelGeom& L,
-                                              int x0, int y0, int16_t* tile, int t) {
-  const int lane = t & 31, wid = t >> 5;
-  const int gx = x0 + lane * 4;
-#pragma unroll
-  for (int j = 0; j < kSegRows / 8; ++j) {
-    const int row = wid + 8 * j, gy = y0 + row;
-    uint2 v = make_uint2(0, 0);
-    if (gy < L.h && gx < L.pitch) v = *reinterpret_cast<const uint2*>(plane + (size_t)gy * L.pitch + gx);
-    uint32_t* d = reinterpret_cast<uint32_t*>(tile + row * kTilePitch16 + lane * 4);
-    d[0] = v.x;
-    d[1] = v.y;
+// Image tile with a one-pixel halo for the Scharr stencil: rows [y0-1, y0+kSegRows], byte
+// columns [x0-4, x0+kStripW+4) (4-byte aligned words); pitch 35 words -> column walks are
+// bank-conflict free.
+constexpr int kImgTileRows = kSegRows + 2;
+constexpr int kImgTileWords = kStripW / 4 + 2;
+constexpr int kImgTilePitch = (kImgTileWords + 1) * 4;  // 140 bytes
+
+__device__ __forceinline__ void load_img_tile_halo(const uint8_t* __restrict__ plane,
+                                                   const LevelGeom& L, int x0, int y0,
+                                                   uint8_t* tile, int t) {
+  for (int i = t; i < kImgTileRows * kImgTileWords; i += 256) {
+    const int row = i / kImgTileWords, j = i % kImgTileWords;
+    const int gy = y0 - 1 + row, gx = x0 - 4 + 4 * j;
+    uint32_t v = 0;
+    if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch)
+      v = *reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx);
+    *reinterpret_cast<uint32_t*>(tile + row * kImgTilePitch + 4 * j) = v;
   }
+}
+
+// Scharr x / y at image pixel (x, y) from the halo tile (Tracker.cpp:1133-1134),
+// BORDER_REFLECT_101 by index mapping: the same integers as K2's gradient_kernel.
+__device__ __forceinline__ void scharr_from_tile(const uint8_t* tile, const LevelGeom& L, int x0,
+                                                 int y0, int x, int y, int& gx, int& gy,
+                                                 int& center) {
+  const int xm = (x == 0) ? 1 : x - 1, xp = (x + 1 >= L.w) ? L.w - 2 : x + 1;
+  const int ym = (y == 0) ? 1 : y - 1, yp = (y + 1 >= L.h) ? L.h - 2 : y + 1;
+  const uint8_t* rm = tile + (ym - (y0 - 1)) * kImgTilePitch - (x0 - 4);
+  const uint8_t* r0 = tile + (y - (y0 - 1)) * kImgTilePitch - (x0 - 4);
+  const uint8_t* rp = tile + (yp - (y0 - 1)) * kImgTilePitch - (x0 - 4);
+  const int a = rm[xm], b = rm[x], cc = rm[xp];
+  const int d = r0[xm], f = r0[xp];
+  const int g = rp[xm], h = rp[x], i = rp[xp];
+  center = r0[x];
+  gx = 3 * (cc - a) + 10 * (f - d) + 3 * (i - g);
+  gy = 3 * (g - a) + 10 * (h - b) + 3 * (i - cc);
 }
 
 __global__ void __launch_bounds__(256)
@@ -145,17 +169,11 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
   if (t == 1023) pools.ncand[(size_t)slot * kMaxLevels + lvl] = warp_tot[31];
 }
 
-constexpr size_t kScatterSmem =
-    2 * (size_t)kSegRows * kTilePitch8 + 2 * (size_t)kSegRows * kTilePitch16 * sizeof(int16_t);
-
 __global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
                     const int* __restrict__ slots) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint8_t* sg = smem;
-  uint8_t* si = sg + kSegRows * kTilePitch8;
-  int16_t* sgx = reinterpret_cast<int16_t*>(si + kSegRows * kTilePitch8);
-  int16_t* sgy = sgx + kSegRows * kTilePitch16;
+  __shared__ __align__(16) uint8_t sg[kSegRows * kTilePitch8];
+  __shared__ __align__(16) uint8_t si[kImgTileRows * kImgTilePitch];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const TileItem it = locate_item(geom, blockIdx.x);
   const int slot = slots[blockIdx.y];
@@ -165,11 +183,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
   const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off;
   const bool has_rec = L.rec_off >= 0;
   load_tile_u8(pools.g + pbase, L, x0, y0, sg, t);
-  if (has_rec) {
-    load_tile_u8(pools.img + pbase, L, x0, y0, si, t);
-    load_tile_i16(pools.gx + pbase, L, x0, y0, sgx, t);
-    load_tile_i16(pools.gy + pbase, L, x0, y0, sgy, t);
-  }
+  if (has_rec) load_img_tile_halo(pools.img + pbase, L, x0, y0, si, t);
   __syncthreads();
   const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
   uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
@@ -194,9 +208,11 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
       if (sel) {
         const uint32_t o = base + __popc(b & lt_mask);
         xy[o] = (uint32_t)x | ((uint32_t)y << 16);
-        if (has_rec)
-          rec[o] = pack_record((uint32_t)x, (uint32_t)y, si[row * kTilePitch8 + c],
-                               sgx[row * kTilePitch16 + c], sgy[row * kTilePitch16 + c]);
+        if (has_rec) {
+          int gx, gy, i1;
+          scharr_from_tile(si, L, x0, y0, x, y, gx, gy, i1);
+          rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
+        }
       }
       base += __popc(b);
     }
@@ -204,19 +220,12 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
 }
 
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(cand_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)kScatterSmem) != cudaSuccess)
-      return -1;
-    attr_set = true;
-  }
   dim3 grid(g.warp_items_total, n);
   cand_count_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
   cand_scan_kernel<<<dim3(g.levels, n), 1024, 0, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scatter_kernel<<<grid, 256, kScatterSmem, st>>>(g, p, d_slots);
+  cand_scatter_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 3;
 }

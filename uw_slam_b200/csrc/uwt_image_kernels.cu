@@ -6,7 +6,10 @@
 //
 // K2 restates Tracker::ApplyGradient (src/Tracker.cpp:1127-1143) for all levels in one
 // launch: Scharr x / y as int16 with BORDER_REFLECT_101, min(|.|,255) and the 0.5/0.5 blend
-// with ties-to-even.  Tiles are staged in shared memory with their halo by the bulk-copy
+// with ties-to-even.  Only the gradient image (u8) is stored: the int16 gradientX_/gradientY_
+// values the tracker needs are recomputed from the image for the selected pixels by the
+// candidate kernel (bit-identical, same stencil), and full planes are written only when a
+// caller reads them back (uwt_get_gradients).  Tiles are staged in shared memory with their halo by the bulk-copy
 // engine (cp.async.bulk + mbarrier), one bulk copy per tile row.  The per-level sum of the
 // gradient image (needed for the candidate threshold, Tracker.cpp:1325-1327) is reduced in
 // the same kernel; the last CTA of a level turns it into the integer threshold.
@@ -194,9 +197,11 @@ __device__ __forceinline__ RowVals row_vals(const uint8_t* srow, int sx, bool le
   return r;
 }
 
+template <bool kPlanes>
 __global__ void __launch_bounds__(256)
 gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                const int* __restrict__ slots) {
+                const int* __restrict__ slots, int16_t* __restrict__ gx_out,
+                int16_t* __restrict__ gy_out) {
   __shared__ __align__(128) uint8_t tile[kTileRows][kTileRowBytes];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t warp_sums[8];
@@ -271,16 +276,17 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
         }
         const size_t o = plane_base + (size_t)y * L.pitch + xg;
         if (nvalid == 4) {
-          *reinterpret_cast<uint2*>(pools.gx + o) =
-              make_uint2((vx[0] & 0xFFFF) | (vx[1] << 16), (vx[2] & 0xFFFF) | (vx[3] << 16));
-          *reinterpret_cast<uint2*>(pools.gy + o) =
-              make_uint2((vy[0] & 0xFFFF) | (vy[1] << 16), (vy[2] & 0xFFFF) | (vy[3] << 16));
           *reinterpret_cast<uint32_t*>(pools.g + o) = gq;
         } else {
+          for (int i = 0; i < nvalid; ++i) pools.g[o + i] = (uint8_t)(gq >> (8 * i));
+        }
+        if (kPlanes) {
+          // gradientX_/gradientY_ planes are materialised only on request (read-back): the
+          // tracker itself consumes the gradients through the packed candidate records
+          const size_t po = (size_t)L.plane_off + (size_t)y * L.pitch + xg;
           for (int i = 0; i < nvalid; ++i) {
-            pools.gx[o + i] = (int16_t)vx[i];
-            pools.gy[o + i] = (int16_t)vy[i];
-            pools.g[o + i] = (uint8_t)(gq >> (8 * i));
+            gx_out[po + i] = (int16_t)vx[i];
+            gy_out[po + i] = (int16_t)vy[i];
           }
         }
         rm = r0;
@@ -329,9 +335,13 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
   }
 }
 
-int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st) {
+int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
+                    int16_t* gx_out, int16_t* gy_out) {
   dim3 grid(g.grad_tiles_total, n);
-  gradient_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
+  if (gx_out && gy_out)
+    gradient_kernel<true><<<grid, 256, 0, st>>>(g, p, d_slots, gx_out, gy_out);
+  else
+    gradient_kernel<false><<<grid, 256, 0, st>>>(g, p, d_slots, nullptr, nullptr);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

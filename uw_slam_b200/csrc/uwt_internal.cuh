@@ -54,8 +54,6 @@ struct Geom {
 // Device memory pools, indexed [slot].
 struct Pools {
   uint8_t* img;         // [slot][plane_elems]
-  int16_t* gx;          // [slot][plane_elems]
-  int16_t* gy;          // [slot][plane_elems]
   uint8_t* g;           // [slot][plane_elems]
   uint32_t* gpart;      // [slot][tile_elems]   per-tile sums of g
   uint32_t* ticket;     // [slot][levels]       last-block tickets (self-resetting)
@@ -91,7 +89,8 @@ constexpr int kShardMaxGrid = 148 * 2;
 // kernel launchers (each returns the number of kernels launched, or <0 on launch error)
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
                    size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st);
-int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
+int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
+                    int16_t* gx_out = nullptr, int16_t* gy_out = nullptr);
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
 int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
                     cudaStream_t st);

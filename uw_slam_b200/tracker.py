@@ -293,6 +293,23 @@ class Tracker:
                                                  pts.shape[0], C.byref(n)))
         return pts[:n.value]
 
+    def get_records(self, slot, lvl):
+        """Decoded packed records of an optimised level: dict of x, y, i1, gx, gy arrays."""
+        n = C.c_int(0)
+        self._check(self._lib.uwt_get_records(self._h, slot, lvl, None, 0, C.byref(n)))
+        buf = np.zeros(max(n.value, 1), np.uint64)
+        self._check(self._lib.uwt_get_records(self._h, slot, lvl,
+                                              buf.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              buf.size, C.byref(n)))
+        r = buf[:n.value]
+
+        def s13(v):
+            v = v.astype(np.int64) & 0x1FFF
+            return np.where(v >= 4096, v - 8192, v).astype(np.int32)
+        return {"x": (r & 0xFFF).astype(np.int32), "y": ((r >> 12) & 0xFFF).astype(np.int32),
+                "i1": ((r >> 24) & 0xFF).astype(np.int32), "gx": s13(r >> 32),
+                "gy": s13(r >> 45)}
+
     def get_trace(self, index=0, cap=512):
         buf = (L.IterTrace * cap)()
         n = C.c_int(0)
