@@ -233,7 +233,8 @@ def run_ours(args):
 
     t = U.Tracker(False)
     t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
-                        max_frames=2 * B, device=local_rank, cluster_size=args.cluster)
+                        max_frames=2 * B, device=local_rank, cluster_size=args.cluster,
+                        flags=(L.FLAG_DMMA_ACCUM if args.dmma_accum else 0))
     stream = torch.cuda.ExternalStream(t.stream_ptr(), device=dev)
     slots_a, slots_b = list(range(B)), list(range(B, 2 * B))
     frame_bytes = w * h
@@ -406,6 +407,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="sequences per GPU")
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per problem (0 = auto)")
+    ap.add_argument("--dmma-accum", action="store_true",
+                    help="A/B: Gram accumulator in fp64 DMMA fragments (slower; off by default)")
     ap.add_argument("--cpu-sequences", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

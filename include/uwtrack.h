@@ -52,6 +52,10 @@ extern "C" {
 
 /* cfg.flags */
 #define UWT_FLAG_TRACE 1u /* record a per-iteration trace (uwt_get_trace); debugging/parity */
+/* A/B switch: hold the 8x8 Gram accumulator [J | 50r]^T [J | 50r] in fp64 tensor-core (DMMA
+ * m8n8k4) fragments per warp instead of 27 fp64 registers per thread.  Bit-identical results;
+ * measured SLOWER on B200 (1.94 vs 1.19 ms per 128 problems), so it is off by default. */
+#define UWT_FLAG_DMMA_ACCUM 2u
 
 typedef struct uwt_tracker uwt_tracker;
 

@@ -125,10 +125,10 @@ def test_warp_function_matches_oracle(oracle, calib):
     t.close()
 
 
-def run_both(oracle, calib, prev, cur, **cfg):
+def run_both(oracle, calib, prev, cur, extra_flags=0, **cfg):
     import uw_slam_b200._lib as L
     w, h, fx, fy, cx, cy = synth.CALIB[calib]
-    t = make_tracker(calib, flags=L.FLAG_TRACE, **cfg)
+    t = make_tracker(calib, flags=L.FLAG_TRACE | extra_flags, **cfg)
     fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
     t.ApplyGradient(fp)
     t.ObtainCandidatePoints(fp)
@@ -180,6 +180,18 @@ def test_cluster_sizes_agree_with_oracle(oracle, pairs, cluster):
     pose, _, trace, opose, _, otrace = run_both(oracle, "tum", prev, cur, cluster_size=cluster)
     assert_trace_equal(trace, otrace)
     assert np.array_equal(pose, opose)
+
+
+def test_dmma_accumulator_variant_matches_oracle(oracle, pairs):
+    import uw_slam_b200._lib as L
+    prev, cur = pairs("tum", 5)
+    pose, _, trace, opose, _, otrace = run_both(oracle, "tum", prev, cur,
+                                                extra_flags=L.FLAG_DMMA_ACCUM)
+    assert_trace_equal(trace, otrace)
+    assert np.array_equal(pose, opose)
+    pose, _, trace, opose, _, otrace = run_both(oracle, "tum", prev, cur, cluster_size=1,
+                                                extra_flags=L.FLAG_DMMA_ACCUM)
+    assert_trace_equal(trace, otrace)
 
 
 def test_batch_of_independent_pairs(oracle, pairs):

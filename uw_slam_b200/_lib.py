@@ -11,6 +11,7 @@ MAX_LEVELS = 7
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
 SOLVE_LU, SOLVE_INVERSE = 0, 1
 FLAG_TRACE = 1
+FLAG_DMMA_ACCUM = 2
 KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 
 

@@ -634,12 +634,13 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   io.trace_cap = t->trace_cap;
   int cluster = pick_cluster(t, n);
   ProfSpan span(t, UWT_K_ESTIMATE);
-  int k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream);
+  const int variant = (t->cfg.flags & UWT_FLAG_DMMA_ACCUM) ? UWT_EST_MMA : UWT_EST_REGISTERS;
+  int k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream, variant);
   while (k < 0 && cluster > 1) {  // a 16-CTA cluster may not be schedulable on every part
     cudaGetLastError();
     cluster /= 2;
     t->max_cluster = cluster;
-    k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream);
+    k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream, variant);
   }
   if (k < 0) return fail(t, UWT_E_CUDA, "estimate kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));

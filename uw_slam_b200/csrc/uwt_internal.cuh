@@ -92,8 +92,10 @@ int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, con
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
                     int16_t* gx_out = nullptr, int16_t* gy_out = nullptr);
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
+constexpr int UWT_EST_MMA = 0;        // Gram accumulator in fp64 tensor-core fragments
+constexpr int UWT_EST_REGISTERS = 1;  // 27 fp64 register accumulators per thread
 int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
-                    cudaStream_t st);
+                    cudaStream_t st, int variant);
 int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, double* partials,
                             double* out32, int grid, cudaStream_t stream);
 int launch_shard_update(const Geom& g, const Pools& p, ShardState* st, const double* sums32,
