@@ -157,6 +157,22 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
 int uwt_shard_accumulate(uwt_tracker* t, double* d_sums32);
 int uwt_shard_update(uwt_tracker* t, const double* d_sums32, int* done);
 int uwt_shard_result(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats);
+/* Fused compute + collective form of the same mode: one persistent kernel per rank runs the
+ * whole loop and all-reduces the 32 sums per sweep by storing them into the peers' mailboxes
+ * over NVLink (no NCCL call, no host round trip per sweep).  Setup once per group:
+ *   every rank: uwt_shard_ipc_export -> 64-byte handle; all-gather the handles (any transport);
+ *   every rank: uwt_shard_ipc_connect(t, rank, nranks, handles)      [ranks in other processes]
+ *   or uwt_shard_connect_local(t, rank, nranks, peers)               [handles of one process]
+ * then per estimate, on every rank: uwt_shard_estimate_fused_async + _wait (all ranks must
+ * call it; a rank whose peers never arrive fails after a bounded wait instead of hanging).
+ * grid = CTAs of the persistent kernel (0 = 148, one per SM). */
+int uwt_shard_ipc_handle_size(void);
+int uwt_shard_ipc_export(uwt_tracker* t, void* handle_out);
+int uwt_shard_ipc_connect(uwt_tracker* t, int rank, int nranks, const void* all_handles);
+int uwt_shard_connect_local(uwt_tracker* t, int rank, int nranks, uwt_tracker* const* peers);
+int uwt_shard_estimate_fused_async(uwt_tracker* t, int prev_slot, int cur_slot,
+                                   const float* init_pose7, int grid);
+int uwt_shard_estimate_fused_wait(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats);
 /* Tracker::WarpFunction on host points (n x 4 floats [x y Z W]) at a pyramid level. */
 int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,
                     float* out4);

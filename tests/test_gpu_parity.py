@@ -302,3 +302,46 @@ def test_sharded_mode_emulated_ranks_match_oracle(oracle, pairs, nranks):
         assert np.array_equal(p, opose)
     for t in ts:
         t.close()
+
+
+def test_fused_sharded_single_rank_equals_estimate_pose(pairs):
+    from uw_slam_b200.sharded import connect_fused, estimate_pose_sharded_fused
+    calib = "tum"
+    prev, cur = pairs(calib, 4)
+    t = make_tracker(calib)
+    fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    ref_pose, ref_stats = t.EstimatePose(fp, fc, return_stats=True)
+    connect_fused(t)
+    for _ in range(3):  # sequence numbers keep running across calls
+        pose, stats = estimate_pose_sharded_fused(t, 0, 1)
+        assert np.array_equal(pose, ref_pose[0])
+        assert list(stats.iterations)[:5] == list(ref_stats[0].iterations)[:5]
+    t.close()
+
+
+def test_fused_sharded_two_emulated_ranks_match_oracle(oracle, pairs):
+    # two handles on ONE GPU play two ranks: their persistent kernels run concurrently (64 CTAs
+    # each) and exchange the sums through each other's mailboxes, exactly as two GPUs would
+    # over NVLink.  Every wait in the kernel is bounded, so a failure cannot hang the device.
+    calib = "euroc"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    prev, cur = pairs(calib, 6)
+    ts = [make_tracker(calib) for _ in range(2)]
+    for t in ts:
+        fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+        t.ApplyGradient(fp)
+        t.ObtainCandidatePoints(fp)
+    for r, t in enumerate(ts):
+        t.ShardConnectLocal(r, ts)
+    rp, rc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
+    opose, _, _ = oracle.estimate_pose(oracle.default_params(w, h, fx, fy, cx, cy), rp, rc)
+    for _ in range(2):
+        for t in ts:
+            t.ShardEstimateFusedAsync(0, 1, grid=64)
+        poses = [t.ShardEstimateFusedWait()[0] for t in ts]
+        assert np.array_equal(poses[0], poses[1])
+        assert np.array_equal(poses[0], opose)
+    for t in ts:
+        t.close()

@@ -174,7 +174,21 @@ def shard4k(args, torch, dist, rank, local_rank, world):
         ref = t.EstimatePose([0], [1])
     t.synchronize()
     dt_single = (time.perf_counter() - t1) / reps
+    # fused form: one persistent kernel per rank, all-reduce over peer memory inside the kernel
+    from uw_slam_b200.sharded import connect_fused, estimate_pose_sharded_fused
+    connect_fused(t)
+    fpose, _ = estimate_pose_sharded_fused(t, 0, 1)
+    if world > 1:
+        dist.barrier()
+    t2 = time.perf_counter()
+    for _ in range(reps):
+        t.ShardEstimateFusedAsync(0, 1)
+    fpose, _ = t.ShardEstimateFusedWait()
+    dt_fused = (time.perf_counter() - t2) / reps
     res = {"metric": "GN pose estimate of one 3840x2160 pair, candidate list sharded over ranks",
+           "ms_per_estimate_fused_peer_allreduce": 1e3 * dt_fused,
+           "us_per_sweep_fused": 1e6 * dt_fused / sweeps,
+           "fused_pose_equals_single_gpu_kernel": bool(np.array_equal(fpose, ref[0])),
            "n_gpus": world, "ms_per_estimate_sharded": 1e3 * dt, "sweeps": sweeps,
            "us_per_sweep_sharded": 1e6 * dt / sweeps,
            "ms_per_estimate_single_kernel_1gpu": 1e3 * dt_single,

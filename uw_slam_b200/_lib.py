@@ -71,6 +71,12 @@ SIGNATURES = {
     "uwt_shard_accumulate": (C.c_int, [_H, C.c_void_p]),
     "uwt_shard_update": (C.c_int, [_H, C.c_void_p, _ip]),
     "uwt_shard_result": (C.c_int, [_H, _fp, C.POINTER(TrackStats)]),
+    "uwt_shard_ipc_handle_size": (C.c_int, []),
+    "uwt_shard_ipc_export": (C.c_int, [_H, C.c_void_p]),
+    "uwt_shard_ipc_connect": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "uwt_shard_connect_local": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(_H)]),
+    "uwt_shard_estimate_fused_async": (C.c_int, [_H, C.c_int, C.c_int, _fp, C.c_int]),
+    "uwt_shard_estimate_fused_wait": (C.c_int, [_H, _fp, C.POINTER(TrackStats)]),
     "uwt_warp_points": (C.c_int, [_H, _fp, C.c_int, _fp, C.c_int, _fp]),
     "uwt_get_image": (C.c_int, [_H, C.c_int, C.c_int, _u8p]),
     "uwt_get_gradients": (C.c_int, [_H, C.c_int, C.c_int, _i16p, _i16p, _u8p]),

@@ -62,6 +62,12 @@ struct uwt_tracker {
   int* d_shard_done = nullptr;
   int* h_shard_done = nullptr;  // pinned
   bool shard_active = false;
+  // fused (in-kernel all-reduce) sharded mode
+  ShardFused* d_fused = nullptr;
+  ShardMailbox* d_mailbox = nullptr;
+  ShardFused h_fused;                 // host mirror of the peer table
+  void* ipc_opened[kShardMaxRanks] = {};
+  int fused_rank = -1, fused_nranks = 0;
   float* d_out_poses = nullptr;
   uwt_track_stats* d_stats = nullptr;
   float* h_out_poses = nullptr;       // pinned
@@ -254,6 +260,10 @@ void destroy_impl(uwt_tracker* t) {
     if (t->stage_free[i]) cudaEventDestroy(t->stage_free[i]);
   }
   if (t->poses_ready) cudaEventDestroy(t->poses_ready);
+  for (void* p : t->ipc_opened)
+    if (p) cudaIpcCloseMemHandle(p);
+  cudaFree(t->d_fused);
+  cudaFree(t->d_mailbox);
   cudaFree(t->d_shard);
   cudaFree(t->d_shard_partials);
   cudaFree(t->d_shard_done);
@@ -384,6 +394,11 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   }
   CREATE_CUDA(cudaEventCreateWithFlags(&t->poses_ready, cudaEventDisableTiming));
   CREATE_CUDA(cudaMalloc(&t->d_shard, sizeof(ShardState)));
+  CREATE_CUDA(cudaMalloc(&t->d_fused, sizeof(ShardFused)));
+  CREATE_CUDA(cudaMalloc(&t->d_mailbox, sizeof(ShardMailbox)));
+  CREATE_CUDA(cudaMemsetAsync(t->d_fused, 0, sizeof(ShardFused), t->stream));
+  CREATE_CUDA(cudaMemsetAsync(t->d_mailbox, 0, sizeof(ShardMailbox), t->stream));
+  std::memset(&t->h_fused, 0, sizeof(t->h_fused));
   CREATE_CUDA(cudaMalloc(&t->d_shard_partials, sizeof(double) * 32 * kShardMaxGrid));
   CREATE_CUDA(cudaMalloc(&t->d_shard_done, sizeof(int)));
   CREATE_CUDA(cudaHostAlloc(&t->h_shard_done, sizeof(int), cudaHostAllocDefault));
@@ -745,6 +760,107 @@ int uwt_shard_result(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats) {
   if (out_pose7) std::memcpy(out_pose7, s.pose, sizeof(s.pose));
   if (stats) *stats = s.stats;
   return UWT_OK;
+}
+
+int uwt_shard_ipc_handle_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int uwt_shard_ipc_export(uwt_tracker* t, void* handle_out) {
+  if (!t || !handle_out) return UWT_E_INVALID;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  cudaIpcMemHandle_t h;
+  UWT_CUDA(t, cudaIpcGetMemHandle(&h, t->d_mailbox));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return UWT_OK;
+}
+
+static int fused_publish(uwt_tracker* t, int rank, int nranks) {
+  t->fused_rank = rank;
+  t->fused_nranks = nranks;
+  // reset the sequence state: every rank does this at connect time, before any sweep
+  t->h_fused.seq = 0;
+  t->h_fused.generation = 0;
+  t->h_fused.error = 0;
+  UWT_CUDA(t, cudaMemsetAsync(t->d_mailbox, 0, sizeof(ShardMailbox), t->stream));
+  UWT_CUDA(t, cudaMemcpyAsync(t->d_fused, &t->h_fused, sizeof(ShardFused), cudaMemcpyHostToDevice,
+                              t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  return UWT_OK;
+}
+
+int uwt_shard_ipc_connect(uwt_tracker* t, int rank, int nranks, const void* all_handles) {
+  if (!t) return UWT_E_INVALID;
+  if (nranks < 1 || nranks > kShardMaxRanks || rank < 0 || rank >= nranks || !all_handles)
+    return fail(t, UWT_E_INVALID, "bad rank %d / nranks %d (max %d)", rank, nranks, kShardMaxRanks);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  for (void*& p : t->ipc_opened)
+    if (p) {
+      cudaIpcCloseMemHandle(p);
+      p = nullptr;
+    }
+  const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      t->h_fused.peer[r] = t->d_mailbox;
+    } else {
+      void* p = nullptr;
+      UWT_CUDA(t, cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
+      t->ipc_opened[r] = p;
+      t->h_fused.peer[r] = static_cast<ShardMailbox*>(p);
+    }
+  }
+  return fused_publish(t, rank, nranks);
+}
+
+int uwt_shard_connect_local(uwt_tracker* t, int rank, int nranks, uwt_tracker* const* peers) {
+  if (!t) return UWT_E_INVALID;
+  if (nranks < 1 || nranks > kShardMaxRanks || rank < 0 || rank >= nranks || !peers)
+    return fail(t, UWT_E_INVALID, "bad rank %d / nranks %d (max %d)", rank, nranks, kShardMaxRanks);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  for (int r = 0; r < nranks; ++r) {
+    if (!peers[r]) return fail(t, UWT_E_INVALID, "peer %d is NULL", r);
+    if (peers[r]->cfg.device != t->cfg.device) {
+      int can = 0;
+      UWT_CUDA(t, cudaDeviceCanAccessPeer(&can, t->cfg.device, peers[r]->cfg.device));
+      if (!can) return fail(t, UWT_E_CUDA, "device %d cannot access peer %d", t->cfg.device,
+                            peers[r]->cfg.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->cfg.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(t, UWT_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    t->h_fused.peer[r] = peers[r]->d_mailbox;
+  }
+  return fused_publish(t, rank, nranks);
+}
+
+int uwt_shard_estimate_fused_async(uwt_tracker* t, int prev_slot, int cur_slot,
+                                   const float* init_pose7, int grid) {
+  if (!t) return UWT_E_INVALID;
+  if (t->fused_rank < 0)
+    return fail(t, UWT_E_STATE, "call uwt_shard_ipc_connect / uwt_shard_connect_local first");
+  int rc = uwt_shard_begin(t, prev_slot, cur_slot, t->fused_rank, t->fused_nranks, init_pose7);
+  if (rc) return rc;
+  if (grid <= 0) grid = 148;
+  if (grid > kShardMaxGrid) grid = kShardMaxGrid;
+  ProfSpan span(t, UWT_K_ESTIMATE);
+  const int k = launch_shard_fused(t->geom, t->pools, t->d_shard, t->d_fused, t->d_mailbox,
+                                   t->d_shard_partials, grid, t->stream);
+  if (k < 0) return fail(t, UWT_E_CUDA, "fused shard kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  span.done(k);
+  return UWT_OK;
+}
+
+int uwt_shard_estimate_fused_wait(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats) {
+  if (!t) return UWT_E_INVALID;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  ShardFused f;
+  UWT_CUDA(t, cudaMemcpy(&f, t->d_fused, sizeof(f), cudaMemcpyDeviceToHost));
+  if (f.error)
+    return fail(t, UWT_E_CUDA, "fused sharded estimate: a peer did not arrive (bounded wait expired)");
+  return uwt_shard_result(t, out_pose7, stats);
 }
 
 int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,

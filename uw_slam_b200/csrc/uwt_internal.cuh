@@ -85,6 +85,22 @@ struct ShardState {
   uwt_track_stats stats;
 };
 constexpr int kShardMaxGrid = 148 * 2;
+constexpr int kShardMaxRanks = 16;
+
+// Mailbox of the fused (in-kernel) all-reduce: peers store their 32 partial sums and a sequence
+// flag directly into this rank's copy over NVLink (IPC- or peer-mapped memory).
+struct ShardMailbox {
+  double sums[2][kShardMaxRanks][32];          // [parity][source rank][value]
+  unsigned long long flag[2][kShardMaxRanks];  // sequence number of the sweep the sums belong to
+};
+
+// Control block of the persistent fused kernel (local device memory).
+struct ShardFused {
+  unsigned long long seq;        // sweeps completed so far on this handle (monotonic)
+  unsigned int generation;       // grid barrier: sweeps whose update is published
+  unsigned int error;            // != 0: a bounded wait expired
+  ShardMailbox* peer[kShardMaxRanks];  // peer[r] = rank r's mailbox as mapped in this process
+};
 
 // kernel launchers (each returns the number of kernels launched, or <0 on launch error)
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
@@ -100,6 +116,8 @@ int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, doubl
                             double* out32, int grid, cudaStream_t stream);
 int launch_shard_update(const Geom& g, const Pools& p, ShardState* st, const double* sums32,
                         int* done_out, cudaStream_t stream);
+int launch_shard_fused(const Geom& g, const Pools& p, ShardState* st, ShardFused* ctl,
+                       ShardMailbox* mine, double* partials, int grid, cudaStream_t stream);
 int launch_warp_points(const Geom& g, const float* d_pts4, int n, const float* d_pose7, int level,
                        float* d_out4, cudaStream_t st);
 

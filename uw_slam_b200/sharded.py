@@ -64,3 +64,33 @@ def estimate_pose_sharded(backend, group=None, max_sweeps=10_000):
                 break
     pose, stats = backend.result()
     return pose, stats, sweeps
+
+
+def connect_fused(tracker, group=None):
+    """One-time setup of the fused (in-kernel all-reduce) sharded mode: exchange the CUDA IPC
+    handles of the per-rank mailboxes with an all-gather and map the peers' mailboxes."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    mine = tracker.ShardIpcExport()
+    if world == 1:
+        tracker.ShardIpcConnect(0, 1, mine)
+        return rank, world
+    dev = torch.device("cuda", tracker.cfg.device)
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    handles = b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+    tracker.ShardIpcConnect(rank, world, handles)
+    dist.barrier(group=group)  # nobody starts a sweep before every mailbox is mapped + zeroed
+    return rank, world
+
+
+def estimate_pose_sharded_fused(tracker, prev_slot, cur_slot, init_pose=None, grid=0):
+    """Whole sharded Gauss-Newton loop in ONE kernel per rank; the per-sweep all-reduce happens
+    inside the kernel through peer-mapped mailboxes.  Call on every rank of the group."""
+    tracker.ShardEstimateFusedAsync(prev_slot, cur_slot, init_pose, grid)
+    return tracker.ShardEstimateFusedWait()

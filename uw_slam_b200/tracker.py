@@ -249,6 +249,36 @@ class Tracker:
         self._check(self._lib.uwt_shard_result(self._h, out.ctypes.data_as(L._fp), C.byref(st)))
         return out, st
 
+    # -- fused (in-kernel all-reduce over peer memory) sharded mode -------------------------
+    def ShardIpcExport(self):
+        n = self._lib.uwt_shard_ipc_handle_size()
+        buf = (C.c_uint8 * n)()
+        self._check(self._lib.uwt_shard_ipc_export(self._h, buf))
+        return bytes(buf)
+
+    def ShardIpcConnect(self, rank, nranks, handles_bytes):
+        buf = (C.c_uint8 * len(handles_bytes)).from_buffer_copy(handles_bytes)
+        self._check(self._lib.uwt_shard_ipc_connect(self._h, rank, nranks, buf))
+
+    def ShardConnectLocal(self, rank, peers):
+        arr = (L._H * len(peers))(*[p._h for p in peers])
+        self._check(self._lib.uwt_shard_connect_local(self._h, rank, len(peers), arr))
+
+    def ShardEstimateFusedAsync(self, prev_slot, cur_slot, init_pose=None, grid=0):
+        ip = None
+        if init_pose is not None:
+            self._ip = np.ascontiguousarray(init_pose, np.float32)
+            ip = self._ip.ctypes.data_as(L._fp)
+        self._check(self._lib.uwt_shard_estimate_fused_async(self._h, prev_slot, cur_slot, ip,
+                                                             grid))
+
+    def ShardEstimateFusedWait(self):
+        out = np.empty(7, np.float32)
+        st = L.TrackStats()
+        self._check(self._lib.uwt_shard_estimate_fused_wait(self._h, out.ctypes.data_as(L._fp),
+                                                            C.byref(st)))
+        return out, st
+
     def synchronize(self):
         self._check(self._lib.uwt_synchronize(self._h))
 
