@@ -348,6 +348,23 @@ def run_ours(args):
     kernels["estimate"]["us_per_gn_sweep_per_problem"] = \
         1e3 * est_ms * B / max(sweeps, 1) if sweeps else None
 
+    # ---- single-problem latency: one pair alone on the GPU (16-CTA cluster) ----
+    prime()
+    upload(1, slots_b, False)
+    t.EstimatePose([0], [B])
+    t.profile(True)
+    reps1 = 20
+    for _ in range(reps1):
+        _, st1 = t.EstimatePose([0], [B], return_stats=True)
+    prof1 = t.profile_read()
+    t.profile(False)
+    sweeps1 = sum(st1[0].evaluations)
+    gn_us = {"single_problem_latency_us_per_sweep": 1e3 * prof1["estimate"][0] / (reps1 * sweeps1),
+             "single_problem_estimate_us": 1e3 * prof1["estimate"][0] / reps1,
+             "batched_us_per_sweep_per_problem": 1e3 * est_ms * B / max(sweeps, 1),
+             "batched_amortised_us_per_sweep": 1e3 * est_ms / max(sweeps, 1),
+             "sweeps_per_track": sweeps / max(len(stats_acc) * B, 1)}
+
     line = None
     if rank == 0:
         value = world * B * K / (ms * 1e-3)
@@ -376,6 +393,7 @@ def run_ours(args):
                          "avg_launch_ms": est_ms / max(est_launches, 1),
                          "point_evals_per_launch": point_evals / max(est_launches, 1)},
             "kernels": kernels,
+            "gn_iteration_us": gn_us,
             "wall_s": {"value_loop": wall, "e2e_loop": wall_e},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -6,7 +6,9 @@
 // There is no CPU fallback anywhere in this file: without a usable CUDA device every entry
 // point returns UWT_E_CUDA.
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -68,6 +70,9 @@ struct uwt_tracker {
   ShardFused h_fused;                 // host mirror of the peer table
   void* ipc_opened[kShardMaxRanks] = {};
   int fused_rank = -1, fused_nranks = 0;
+  // private single-rank instance of the fused kernel: whole-GPU path of ONE large problem
+  ShardFused* d_fused_self = nullptr;
+  ShardMailbox* d_mailbox_self = nullptr;
   float* d_out_poses = nullptr;
   uwt_track_stats* d_stats = nullptr;
   float* h_out_poses = nullptr;       // pinned
@@ -264,6 +269,8 @@ void destroy_impl(uwt_tracker* t) {
     if (p) cudaIpcCloseMemHandle(p);
   cudaFree(t->d_fused);
   cudaFree(t->d_mailbox);
+  cudaFree(t->d_fused_self);
+  cudaFree(t->d_mailbox_self);
   cudaFree(t->d_shard);
   cudaFree(t->d_shard_partials);
   cudaFree(t->d_shard_done);
@@ -399,6 +406,15 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   CREATE_CUDA(cudaMemsetAsync(t->d_fused, 0, sizeof(ShardFused), t->stream));
   CREATE_CUDA(cudaMemsetAsync(t->d_mailbox, 0, sizeof(ShardMailbox), t->stream));
   std::memset(&t->h_fused, 0, sizeof(t->h_fused));
+  CREATE_CUDA(cudaMalloc(&t->d_fused_self, sizeof(ShardFused)));
+  CREATE_CUDA(cudaMalloc(&t->d_mailbox_self, sizeof(ShardMailbox)));
+  CREATE_CUDA(cudaMemsetAsync(t->d_mailbox_self, 0, sizeof(ShardMailbox), t->stream));
+  {
+    ShardFused self;
+    std::memset(&self, 0, sizeof(self));
+    self.peer[0] = t->d_mailbox_self;
+    CREATE_CUDA(cudaMemcpy(t->d_fused_self, &self, sizeof(self), cudaMemcpyHostToDevice));
+  }
   CREATE_CUDA(cudaMalloc(&t->d_shard_partials, sizeof(double) * 32 * kShardMaxGrid));
   CREATE_CUDA(cudaMalloc(&t->d_shard_done, sizeof(int)));
   CREATE_CUDA(cudaHostAlloc(&t->h_shard_done, sizeof(int), cudaHostAllocDefault));
@@ -629,6 +645,54 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
       return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slots[i]);
   }
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  // ONE large problem (>= 1 Mpixel on the finest optimised level): the persistent whole-GPU
+  // kernel (148 CTAs, grid barrier) beats the 16-CTA cluster (measured at 3840x2160: 187 vs
+  // 336 us); smaller frames stay on the cluster kernel (117 vs 165 us at 1280x1024).
+  {
+    const LevelGeom& Lf = t->geom.lv[t->cfg.last_level];
+    if (n == 1 && t->cfg.cluster_size == 0 && !(t->cfg.flags & UWT_FLAG_TRACE) &&
+        (long long)Lf.w * Lf.h >= (1 << 20)) {
+      ShardState s;
+      std::memset(&s, 0, sizeof(s));
+      const float ident[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
+      std::memcpy(s.pose, init_poses7 ? init_poses7 : ident, sizeof(ident));
+      s.last_error = 50000.0f;
+      s.level = t->cfg.first_level;
+      s.rank = 0;
+      s.nranks = 1;
+      s.prev_slot = prev_slots[0];
+      s.cur_slot = cur_slots[0];
+      ArgRegion* r;
+      if ((rc = acquire(t, &r))) return rc;
+      static_assert(sizeof(ShardState) <= sizeof(float) * 7 * 16, "staging too small");
+      if ((size_t)t->cfg.max_frames * 7 * sizeof(float) >= sizeof(ShardState)) {
+        std::memcpy(r->h_flt, &s, sizeof(s));  // pinned staging: no host sync
+        UWT_CUDA(t, cudaMemcpyAsync(t->d_shard, r->h_flt, sizeof(s), cudaMemcpyHostToDevice,
+                                    t->stream));
+      } else {
+        UWT_CUDA(t, cudaMemcpyAsync(t->d_shard, &s, sizeof(s), cudaMemcpyHostToDevice, t->stream));
+        UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+      }
+      ProfSpan span(t, UWT_K_ESTIMATE);
+      const int k = launch_shard_fused(t->geom, t->pools, t->d_shard, t->d_fused_self,
+                                       t->d_mailbox_self, t->d_shard_partials, 148, t->stream);
+      if (k < 0) return fail(t, UWT_E_CUDA, "fused estimate kernel launch failed: %s",
+                             cudaGetErrorString(cudaGetLastError()));
+      t->launches += k;
+      span.done(k);
+      UWT_CUDA(t, cudaMemcpyAsync(t->h_out_poses, reinterpret_cast<char*>(t->d_shard) +
+                                  offsetof(ShardState, pose), sizeof(float) * 7,
+                                  cudaMemcpyDeviceToHost, t->stream));
+      UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, reinterpret_cast<char*>(t->d_shard) +
+                                  offsetof(ShardState, stats), sizeof(uwt_track_stats),
+                                  cudaMemcpyDeviceToHost, t->stream));
+      UWT_CUDA(t, cudaEventRecord(t->poses_ready, t->stream));
+      if ((rc = release(t, r))) return rc;
+      t->last_n = 1;
+      t->shard_active = false;
+      return UWT_OK;
+    }
+  }
   ArgRegion* r;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, prev_slots, cur_slots))) return rc;
@@ -858,6 +922,10 @@ int uwt_shard_estimate_fused_wait(uwt_tracker* t, float* out_pose7, uwt_track_st
   UWT_CUDA(t, cudaStreamSynchronize(t->stream));
   ShardFused f;
   UWT_CUDA(t, cudaMemcpy(&f, t->d_fused, sizeof(f), cudaMemcpyDeviceToHost));
+  if (getenv("UWT_DEBUG") && f.dbg[5])
+    fprintf(stderr, "[uwt fused] sweeps %llu | cycles/sweep: own-accumulate %llu, until-all-CTAs %llu, "
+            "reduce %llu, mailbox %llu, K5 %llu\n", f.dbg[5], f.dbg[0] / f.dbg[5], f.dbg[1] / f.dbg[5],
+            f.dbg[2] / f.dbg[5], f.dbg[3] / f.dbg[5], f.dbg[4] / f.dbg[5]);
   if (f.error)
     return fail(t, UWT_E_CUDA, "fused sharded estimate: a peer did not arrive (bounded wait expired)");
   return uwt_shard_result(t, out_pose7, stats);

@@ -87,11 +87,12 @@ struct ShardState {
 constexpr int kShardMaxGrid = 148 * 2;
 constexpr int kShardMaxRanks = 16;
 
-// Mailbox of the fused (in-kernel) all-reduce: peers store their 32 partial sums and a sequence
-// flag directly into this rank's copy over NVLink (IPC- or peer-mapped memory).
+// Mailbox of the fused (in-kernel) all-reduce: peers store their 32 partial sums directly into
+// this rank's copy over NVLink (IPC- or peer-mapped memory).  "LL" protocol: every 8-byte word
+// carries 32 data bits and the 32-bit sequence number of the sweep, so data and flag arrive in
+// ONE atomic 8-byte store and no memory fence is needed on either side; a double takes two words.
 struct ShardMailbox {
-  double sums[2][kShardMaxRanks][32];          // [parity][source rank][value]
-  unsigned long long flag[2][kShardMaxRanks];  // sequence number of the sweep the sums belong to
+  unsigned long long ll[2][kShardMaxRanks][64];  // [parity][source rank][2 * value + half]
 };
 
 // Control block of the persistent fused kernel (local device memory).
@@ -99,6 +100,7 @@ struct ShardFused {
   unsigned long long seq;        // sweeps completed so far on this handle (monotonic)
   unsigned int generation;       // grid barrier: sweeps whose update is published
   unsigned int error;            // != 0: a bounded wait expired
+  unsigned long long dbg[8];     // leader-phase cycle counters (profiling aid)
   ShardMailbox* peer[kShardMaxRanks];  // peer[r] = rank r's mailbox as mapped in this process
 };
 
