@@ -50,6 +50,14 @@ extern "C" {
 #define UWT_SOLVE_LU 0      /* cv::solve(A, b, DECOMP_LU) -- what cv::MatExpr folds it to */
 #define UWT_SOLVE_INVERSE 1 /* cv::invert(A, DECOMP_LU) followed by the 6x6 * 6x1 gemm    */
 
+/* Residual weights W of the Gauss-Newton step (src/Tracker.cpp:495-496). */
+#define UWT_WEIGHT_IDENTITY 0 /* IdentityWeights: what the reference ships (Tracker.cpp:495)    */
+#define UWT_WEIGHT_TUKEY 1    /* TukeyFunctionWeights with the MAD scale, the commented alternative
+                                 (Tracker.cpp:496, 1571-1594, 1607-1654): a second pass per sweep
+                                 builds the residual histogram the median / MAD come from        */
+#define UWT_WEIGHT_HUBER 2    /* north-star option (not in the reference): w = 1 for |r| <= delta,
+                                 delta/|r| beyond; sqrt(w) scales Jacobian rows and residuals    */
+
 /* cfg.flags */
 #define UWT_FLAG_TRACE 1u /* record a per-iteration trace (uwt_get_trace); debugging/parity */
 /* A/B switch: hold the 8x8 Gram accumulator [J | 50r]^T [J | 50r] in fp64 tensor-core (DMMA
@@ -75,6 +83,8 @@ typedef struct {
   int cluster_size;          /* CTAs cooperating on ONE problem in uwt_estimate_pose:
                                 0 = choose from n (1 for large batches, 16 for n == 1)   */
   unsigned flags;            /* UWT_FLAG_*                                               */
+  int weight_mode;           /* UWT_WEIGHT_* (0 = reference)                             */
+  float huber_delta;         /* UWT_WEIGHT_HUBER threshold in gray levels                */
 } uwt_config;
 
 typedef struct {

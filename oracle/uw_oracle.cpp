@@ -242,6 +242,66 @@ void accumulate(const float* J, const float* r50, const unsigned char* valid, in
   }
 }
 
+// saturate_cast<uchar>(float): cvRound (ties to even) then clamp, as Mat::convertTo(CV_8UC1)
+inline int sat_u8(float v) {
+  const int i = (int)std::nearbyintf(v);
+  return i < 0 ? 0 : (i > 255 ? 255 : i);
+}
+
+// Tracker::MedianMat, Tracker.cpp:1571-1594
+float median_mat(const float* v, int n) {
+  float hist[256];  // calcHist returns CV_32F counts
+  {
+    int cnt[256] = {0};
+    for (int i = 0; i < n; ++i) ++cnt[sat_u8(v[i])];  // convertTo + calcHist, :1573,1585
+    for (int i = 0; i < 256; ++i) hist[i] = (float)cnt[i];
+  }
+  const float m = (float)(n / 2);  // :1575 integer division, stored float
+  int bin = 0;
+  float med = -1.0f;
+  for (int i = 0; i < 256 && med < 0.0f; ++i) {  // :1587-1591
+    bin += (int)std::nearbyintf(hist[i]);        // cvRound
+    if ((float)bin > m && med < 0.0f) med = (float)i;
+  }
+  return med;
+}
+
+// Tracker::MedianAbsoluteDeviation, Tracker.cpp:1607-1619
+float mad_scale(const float* v, int n) {
+  const float c = 1.4826f;
+  const float median = median_mat(v, n);
+  std::vector<float> dev(n);
+  for (int i = 0; i < n; ++i) dev[i] = std::fabs(v[i] - median);  // :1613
+  const float MAD = median_mat(dev.data(), n);                    // :1616
+  return c * MAD;
+}
+
+// Tracker::TukeyFunctionWeights, Tracker.cpp:1626-1654
+void tukey_weights(const float* v, int n, float* w) {
+  const float b = 4.6851f;
+  float MAD = mad_scale(v, n);
+  if (MAD == 0) MAD = 1;              // :1634-1637
+  const float inv_MAD = 1.0 / MAD;    // :1638 (double division, stored float)
+  const float inv_b2 = 1.0 / (b * b); // :1639
+  for (int i = 0; i < n; ++i) {
+    const float x = v[i] * inv_MAD;   // :1643
+    if (std::fabs(x) <= b) {
+      const float tukey = (1.0 - (x * x) * inv_b2);  // :1646 (float product, double subtraction)
+      w[i] = tukey * tukey;
+    } else {
+      w[i] = 0.0f;
+    }
+  }
+}
+
+// Huber weights (north-star option, ARITHMETIC.md R4)
+void huber_weights(const float* v, int n, float delta, float* w) {
+  for (int i = 0; i < n; ++i) {
+    const float a = std::fabs(v[i]);
+    w[i] = (a <= delta) ? 1.0f : delta / a;
+  }
+}
+
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -268,6 +328,8 @@ void uwo_default_params(uwo_params* p) {
   p->solve_mode = UWO_SOLVE_LU;
   p->accum_mode = UWO_ACCUM_LONGDOUBLE;
   p->threads = 1;
+  p->weight_mode = UWO_WEIGHT_IDENTITY;  // Tracker.cpp:495
+  p->huber_delta = 10.0f;
 }
 
 void uwo_pyr_down(const uint8_t* src, int w, int h, uint8_t* dst) {
@@ -425,6 +487,11 @@ int uwo_lu_invert6(const float* A36, float* Ainv36) {
   return 1;
 }
 
+float uwo_median_mat(const float* v, int n) { return median_mat(v, n); }
+float uwo_mad(const float* v, int n) { return mad_scale(v, n); }
+void uwo_tukey_weights(const float* v, int n, float* w) { tukey_weights(v, n, w); }
+void uwo_huber_weights(const float* v, int n, float delta, float* w) { huber_weights(v, n, delta, w); }
+
 void uwo_build_pyramid(const uwo_params* p, uint8_t* const* images) {
   for (int l = 1; l < p->levels; ++l)
     uwo_pyr_down(images[l - 1], p->width >> (l - 1), p->height >> (l - 1), images[l]);
@@ -432,7 +499,7 @@ void uwo_build_pyramid(const uwo_params* p, uint8_t* const* images) {
 
 // One residual sweep (Tracker.cpp:422-490 + the sums of :559-562) over candidate rows
 // [lo, hi) of one level at pose7.  sums32: 21 upper-triangular J^T J terms, 6 J^T (50 r)
-// terms (b is minus these), sum r^2, N_valid, 3 x 0.  The structure is the reference's: a
+// terms (b is minus these), sum r^2, N_valid, [29] = sum r (r w) when weighted, 2 x 0.  The structure is the reference's: a
 // separate WarpFunction pass, then materialised Jacobian / residual arrays, then the products.
 int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8_t* I2,
                     const int16_t* gx, const int16_t* gy, const float* cand, int lo, int hi,
@@ -448,7 +515,7 @@ int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8
   const int cols = wl[lvl], rows = hl[lvl];
   const float fx = fxl[lvl], fy = fyl[lvl];
   const int threads = p->threads < 1 ? 1 : p->threads;
-  std::vector<float> warped((size_t)n * 4), J((size_t)n * 6), r50(n);
+  std::vector<float> warped((size_t)n * 4), J((size_t)n * 6), r50(n), res(n);
   std::vector<unsigned char> valid(n);
   // --- WarpFunction (separate pass over all points, Tracker.cpp:422) ---
   parallel_chunks(threads, [&](int c) {
@@ -497,6 +564,7 @@ int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8
         for (int q = 0; q < 6; ++q)
           J[(size_t)i * 6 + q] =
               (float)((double)jlx * (double)Jw0[q] + (double)jly * (double)Jw1[q]);
+        res[i] = (float)r;                      // Residuals row, Tracker.cpp:487
         r50[i] = (float)r * p->residual_scale;  // Tracker.cpp:559 (exact)
         valid[i] = 1;
         sum_r2 += (long long)r * r;
@@ -513,6 +581,33 @@ int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8
     n_valid += part_nv[c];
   }
   for (int i = 0; i < 32; ++i) sums32[i] = 0.0;
+  if (p->weight_mode != UWO_WEIGHT_IDENTITY) {
+    // Tracker.cpp:496: W = TukeyFunctionWeights(Residuals) on the valid rows only, in order
+    std::vector<float> rv, wv;
+    rv.reserve(n_valid);
+    for (int i = 0; i < n; ++i)
+      if (valid[i]) rv.push_back(res[i]);
+    wv.resize(rv.size());
+    if (p->weight_mode == UWO_WEIGHT_TUKEY)
+      tukey_weights(rv.data(), (int)rv.size(), wv.data());
+    else
+      huber_weights(rv.data(), (int)rv.size(), p->huber_delta, wv.data());
+    long double esum = 0.0L;
+    size_t j = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!valid[i]) continue;
+      const float w = wv[j++];
+      // Tracker.cpp:500-501: error = inv_num * Residuals^T (Residuals .* W)   (U3: fp64 sum)
+      const float rw = res[i] * w;
+      esum += (long double)((double)res[i] * (double)rw);
+      // Tukey (Kerl-way, Tracker.cpp:554-562): rows of J and the scaled residuals are both
+      // multiplied by w;  Huber: by sqrt(w), i.e. A = sum w J J^T, b = -sum w J (50 r)
+      const float s = (p->weight_mode == UWO_WEIGHT_TUKEY) ? w : std::sqrt(w);
+      for (int q = 0; q < 6; ++q) J[(size_t)i * 6 + q] = s * J[(size_t)i * 6 + q];
+      r50[i] = r50[i] * s;
+    }
+    sums32[29] = (double)esum;
+  }
   // Tracker.cpp:559-562: A = J^T J, b = -J^T (50 r)
   if (p->accum_mode == UWO_ACCUM_LONGDOUBLE)
     accumulate<long double>(J.data(), r50.data(), valid.data(), n, threads, sums32, sums32 + 21);
@@ -539,7 +634,9 @@ int uwo_gn_update(const uwo_params* p, const double* sums32, int k, float* pose7
   }
   // Tracker.cpp:499-502: error = (1/N) r^T r  (U3)
   const float inv_num = 1.0 / n_valid;
-  const float error = (float)((double)inv_num * (double)sum_r2);
+  const float error = (p->weight_mode == UWO_WEIGHT_IDENTITY)
+                          ? (float)((double)inv_num * (double)sum_r2)
+                          : (float)((double)inv_num * sums32[29]);
   if (tr) tr->error = error;
   // Tracker.cpp:508: break test (the update that led here is kept)
   if (error >= *last_error || k == p->max_iterations - 1 ||
@@ -620,7 +717,10 @@ int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
       }
       if (stats && sums[28] > 0) {
         const float inv_num = 1.0 / (int)sums[28];
-        stats->final_error[lvl] = (float)((double)inv_num * (double)(long long)sums[27]);
+        stats->final_error[lvl] =
+            (p->weight_mode == UWO_WEIGHT_IDENTITY)
+                ? (float)((double)inv_num * (double)(long long)sums[27])
+                : (float)((double)inv_num * sums[29]);
         if (!brk) stats->iterations[lvl] = k + 1;
       }
       (void)err_before;

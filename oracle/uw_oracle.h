@@ -27,6 +27,13 @@ extern "C" {
 #define UWO_SOLVE_LU 0      /* cv::solve(A,b,DECOMP_LU): what OpenCV's MatExpr does */
 #define UWO_SOLVE_INVERSE 1 /* cv::invert(A) then gemm: the literal reading         */
 
+/* weight_mode: residual weights W of the Gauss-Newton step (Tracker.cpp:495-496). */
+#define UWO_WEIGHT_IDENTITY 0 /* IdentityWeights: what the reference ships (Tracker.cpp:495)  */
+#define UWO_WEIGHT_TUKEY 1    /* TukeyFunctionWeights + MAD scale: the commented alternative
+                                 (Tracker.cpp:496, 1571-1594, 1607-1654)                       */
+#define UWO_WEIGHT_HUBER 2    /* north-star option, not in the reference: w = 1 (|r| <= d),
+                                 d/|r| otherwise, applied as sqrt(w) to J rows and residuals   */
+
 /* accum_mode: accumulator of the normal equations (docs/ARITHMETIC.md U3). */
 #define UWO_ACCUM_DOUBLE 0     /* sequential fp64 (timed baseline)     */
 #define UWO_ACCUM_LONGDOUBLE 1 /* sequential 80-bit (checker, default) */
@@ -44,6 +51,8 @@ typedef struct {
   int solve_mode;             /* UWO_SOLVE_*                                      */
   int accum_mode;             /* UWO_ACCUM_*                                      */
   int threads;                /* 1 = like the reference; >1 = std::thread over points  */
+  int weight_mode;            /* UWO_WEIGHT_* (Tracker.cpp:495-496)                */
+  float huber_delta;          /* UWO_WEIGHT_HUBER threshold in gray levels         */
 } uwo_params;
 
 /* One record per Gauss-Newton iteration (including the breaking one). */
@@ -91,6 +100,16 @@ void uwo_se3_exp(const float* tangent6, float* pose7);
 void uwo_se3_mul(const float* a7, const float* b7, float* out7);
 void uwo_se3_matrix(const float* pose7, float* m16);
 void uwo_se3_scale_level(const float* pose7, float* out7); /* Tracker.cpp:580-590 */
+
+/* Tracker::MedianMat (Tracker.cpp:1571-1594): convertTo(CV_8UC1) + 256-bin calcHist + first
+ * bin whose cumulative count exceeds n/2.  Returns -1 for n == 0. */
+float uwo_median_mat(const float* v, int n);
+/* Tracker::MedianAbsoluteDeviation (Tracker.cpp:1607-1619): 1.4826 * MedianMat(|v - MedianMat(v)|). */
+float uwo_mad(const float* v, int n);
+/* Tracker::TukeyFunctionWeights (Tracker.cpp:1626-1654): w[i] for residuals v[i]. */
+void uwo_tukey_weights(const float* v, int n, float* w);
+/* Huber weights (north-star option; docs/ARITHMETIC.md R4). */
+void uwo_huber_weights(const float* v, int n, float delta, float* w);
 
 /* cv::solve / cv::invert (DECOMP_LU) on 6x6 f32.  Return 0 if singular. */
 int uwo_lu_solve6(const float* A36, const float* b6, float* x6);

@@ -14,6 +14,7 @@ _SO = os.path.join(_HERE, "libuw_oracle.so")
 MAX_LEVELS = 8
 SOLVE_LU, SOLVE_INVERSE = 0, 1
 ACCUM_DOUBLE, ACCUM_LONGDOUBLE = 0, 1
+WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -24,6 +25,7 @@ class Params(C.Structure):
         ("max_iterations", C.c_int), ("epsilon", C.c_float), ("residual_scale", C.c_float),
         ("gradient_threshold", C.c_double),
         ("solve_mode", C.c_int), ("accum_mode", C.c_int), ("threads", C.c_int),
+        ("weight_mode", C.c_int), ("huber_delta", C.c_float),
     ]
 
 
@@ -76,6 +78,12 @@ def lib():
         L.uwo_lu_solve6.restype = C.c_int
         L.uwo_lu_invert6.argtypes = [f32p, f32p]
         L.uwo_lu_invert6.restype = C.c_int
+        L.uwo_median_mat.argtypes = [f32p, C.c_int]
+        L.uwo_median_mat.restype = C.c_float
+        L.uwo_mad.argtypes = [f32p, C.c_int]
+        L.uwo_mad.restype = C.c_float
+        L.uwo_tukey_weights.argtypes = [f32p, C.c_int, f32p]
+        L.uwo_huber_weights.argtypes = [f32p, C.c_int, C.c_float, f32p]
         L.uwo_estimate_pose.restype = C.c_int
         L.uwo_track_pair.restype = C.c_int
         L.uwo_track_pair.argtypes = [C.POINTER(Params), u8p, u8p, f32p, C.POINTER(Stats),
@@ -97,6 +105,30 @@ def default_params(width=640, height=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5
             raise AttributeError(k)
         setattr(p, k, v)
     return p
+
+
+def median_mat(v):
+    v = np.ascontiguousarray(v, np.float32).ravel()
+    return float(lib().uwo_median_mat(_p(v, C.c_float), v.size))
+
+
+def mad(v):
+    v = np.ascontiguousarray(v, np.float32).ravel()
+    return float(lib().uwo_mad(_p(v, C.c_float), v.size))
+
+
+def tukey_weights(v):
+    v = np.ascontiguousarray(v, np.float32).ravel()
+    w = np.empty(v.size, np.float32)
+    lib().uwo_tukey_weights(_p(v, C.c_float), v.size, _p(w, C.c_float))
+    return w
+
+
+def huber_weights(v, delta):
+    v = np.ascontiguousarray(v, np.float32).ravel()
+    w = np.empty(v.size, np.float32)
+    lib().uwo_huber_weights(_p(v, C.c_float), v.size, float(delta), _p(w, C.c_float))
+    return w
 
 
 def pyr_down(img):

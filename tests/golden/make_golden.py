@@ -103,5 +103,30 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
+def main_robust():
+    """Golden traces of the robust-weight modes: Tukey/MAD as in
+    Tracker.cpp:496,1571-1654 and the Huber option; inputs are regenerated from the seed."""
+    rob = {}
+    for calib, seeds in (("tiny", [0]), ("small", [1, 2]), ("tum", [0, 4])):
+        w, h, fx, fy, cx, cy = synth.CALIB[calib]
+        for s in seeds:
+            prev, cur, _, _ = synth.render_pair(calib, s)
+            fp, fc = O.FrameData(prev), O.FrameData(cur, with_candidates=False)
+            for mode, name in ((O.WEIGHT_TUKEY, "tukey"), (O.WEIGHT_HUBER, "huber")):
+                p = O.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=7.5)
+                pose, st, tr = O.estimate_pose(p, fp, fc)
+                key = "%s_%d_%s" % (calib, s, name)
+                rob[key + "_input_sha"] = np.array([sha(prev), sha(cur)])
+                rob[key + "_final"] = pose
+                rob[key + "_iterations"] = np.array(list(st.iterations)[:5], np.int32)
+                for k, v in trace_arrays(tr).items():
+                    rob[key + "_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "golden_robust.npz"), **rob)
+    print("golden_robust.npz", os.path.getsize(os.path.join(HERE, "golden_robust.npz")) // 1024,
+          "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--robust-only" not in sys.argv:
+        main()
+    main_robust()

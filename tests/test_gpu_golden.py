@@ -84,6 +84,30 @@ def test_big_golden_on_gpu(calib, seed):
     t.close()
 
 
+@pytest.mark.parametrize("calib,seed", [("tiny", 0), ("small", 1), ("small", 2), ("tum", 0),
+                                        ("tum", 4)])
+@pytest.mark.parametrize("name,mode", [("tukey", 1), ("huber", 2)])
+def test_robust_golden_on_gpu(calib, seed, name, mode):
+    # Tukey/MAD (Tracker.cpp:496,1571-1654) and Huber weights
+    from uw_slam_b200 import _lib as L
+    gold = np.load(os.path.join(GOLD, "golden_robust.npz"))
+    key = "%s_%d_%s" % (calib, seed, name)
+    prev, cur, _, _ = synth.render_pair(calib, seed)
+    if [sha(prev), sha(cur)] != list(gold[key + "_input_sha"]):
+        pytest.skip("numpy on this box renders different input bytes than the fixture")
+    t = tracker_for(calib, flags=L.FLAG_TRACE, weight_mode=mode, huber_delta=7.5)
+    fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    pose, stats = t.EstimatePose(fp, fc, return_stats=True)
+    tr = t.get_trace(0)
+    check_trace(gold, key, tr)
+    assert np.array_equal(np.array([x.error for x in tr], np.float32), gold[key + "_error"])
+    assert np.array_equal(pose[0], gold[key + "_final"])
+    assert list(stats[0].iterations)[:5] == list(gold[key + "_iterations"])
+    t.close()
+
+
 CALIB_XML = """<?xml version="1.0"?>
 <opencv_storage>
 <in_width type_id="integer"> {w} </in_width>

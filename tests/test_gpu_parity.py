@@ -135,7 +135,9 @@ def run_both(oracle, calib, prev, cur, extra_flags=0, **cfg):
     pose, stats = t.EstimatePose(fp, fc, return_stats=True)
     trace = t.get_trace(0)
     t.close()
-    p = oracle.default_params(w, h, fx, fy, cx, cy, solve_mode=cfg.get("solve_mode", 0))
+    p = oracle.default_params(w, h, fx, fy, cx, cy, solve_mode=cfg.get("solve_mode", 0),
+                              weight_mode=cfg.get("weight_mode", 0),
+                              huber_delta=cfg.get("huber_delta", 10.0))
     rp, rc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
     opose, ostats, otrace = oracle.estimate_pose(p, rp, rc)
     return pose[0], stats[0], trace, opose, ostats, otrace
@@ -180,6 +182,65 @@ def test_cluster_sizes_agree_with_oracle(oracle, pairs, cluster):
     pose, _, trace, opose, _, otrace = run_both(oracle, "tum", prev, cur, cluster_size=cluster)
     assert_trace_equal(trace, otrace)
     assert np.array_equal(pose, opose)
+
+
+# the robust-weight path (Tracker.cpp:496, 1571-1654) and the Huber option
+@pytest.mark.parametrize("mode,calib,seed,cluster", [
+    (1, "tiny", 0, 0), (1, "small", 1, 0), (1, "tum", 0, 0), (1, "tum", 7, 1), (1, "tum", 3, 4),
+    (1, "euroc", 2, 0), (1, "tum_mono", 5, 0),
+    (2, "small", 0, 0), (2, "tum", 2, 0), (2, "tum", 2, 2), (2, "tum_mono", 5, 0)])
+def test_robust_weights_match_oracle(oracle, pairs, mode, calib, seed, cluster):
+    prev, cur = pairs(calib, seed)
+    pose, stats, trace, opose, ostats, otrace = run_both(
+        oracle, calib, prev, cur, weight_mode=mode, huber_delta=7.5, cluster_size=cluster)
+    assert_trace_equal(trace, otrace)
+    assert list(stats.iterations)[:5] == list(ostats.iterations)[:5]
+    assert np.array_equal(pose, opose)
+    # the weights must actually change the estimate relative to the shipped identity weights
+    pose_id = run_both(oracle, calib, prev, cur, cluster_size=cluster)[0]
+    assert not np.array_equal(pose, pose_id)
+
+
+def test_robust_weights_with_outliers(oracle, pairs):
+    # an occluder in the second frame: Tukey must down-weight it, and still match the oracle
+    prev, cur = pairs("tum", 4)
+    cur = cur.copy()
+    cur[100:220, 200:360] = 255 - cur[100:220, 200:360]
+    for mode in (1, 2):
+        pose, _, trace, opose, _, otrace = run_both(oracle, "tum", prev, cur, weight_mode=mode)
+        assert_trace_equal(trace, otrace)
+        assert np.array_equal(pose, opose)
+
+
+def test_robust_weights_batch_and_rejections(oracle, pairs):
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    calib = "small"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    B = 12
+    t = make_tracker(calib, max_frames=2 * B, weight_mode=L.WEIGHT_TUKEY)
+    prevs = np.stack([pairs(calib, s)[0] for s in range(B)])
+    curs = np.stack([pairs(calib, s)[1] for s in range(B)])
+    fp = t.AddFrames(list(range(B)), prevs)
+    fc = t.AddFrames(list(range(B, 2 * B)), curs)
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    poses = t.EstimatePose(fp, fc)
+    p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=1)
+    for s in range(B):
+        rp = oracle.FrameData(prevs[s])
+        rc = oracle.FrameData(curs[s], with_candidates=False)
+        assert np.array_equal(poses[s], oracle.estimate_pose(p, rp, rc)[0]), s
+    # the sharded single-frame mode is identity-weights only and says so
+    rc = t._lib.uwt_shard_begin(t._h, 0, B, 0, 1, None)
+    assert rc == L.E_INVALID
+    t.close()
+    with pytest.raises(U.UwtError):
+        make_tracker(calib, weight_mode=7)
+    with pytest.raises(U.UwtError):
+        make_tracker(calib, weight_mode=L.WEIGHT_HUBER, huber_delta=0.0)
+    with pytest.raises(U.UwtError):
+        make_tracker(calib, weight_mode=L.WEIGHT_TUKEY, flags=L.FLAG_DMMA_ACCUM)
 
 
 def test_dmma_accumulator_variant_matches_oracle(oracle, pairs):

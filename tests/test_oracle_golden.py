@@ -77,6 +77,27 @@ def test_big_golden(oracle, big, calib, seed):
     assert list(st.iterations)[:5] == list(big[key + "_iterations"])
 
 
+@pytest.fixture(scope="module")
+def robust():
+    return np.load(os.path.join(GOLD, "golden_robust.npz"))
+
+
+@pytest.mark.parametrize("calib,seed", [("tiny", 0), ("small", 1), ("small", 2), ("tum", 0),
+                                        ("tum", 4)])
+@pytest.mark.parametrize("name,mode", [("tukey", 1), ("huber", 2)])
+def test_robust_golden(oracle, robust, calib, seed, name, mode):
+    key = "%s_%d_%s" % (calib, seed, name)
+    prev, cur, _, _ = synth.render_pair(calib, seed)
+    assert [sha(prev), sha(cur)] == list(robust[key + "_input_sha"])
+    fp, fc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=7.5)
+    pose, st, tr = oracle.estimate_pose(p, fp, fc)
+    check_trace(robust, key, tr)
+    assert np.array_equal(pose, robust[key + "_final"])
+    assert list(st.iterations)[:5] == list(robust[key + "_iterations"])
+
+
 def test_accumulator_modes_agree(oracle):
     # fp64-sequential (timed baseline) and 80-bit (checker) accumulation round to the same f32
     calib = "small"
@@ -105,8 +126,9 @@ def np_quat_to_R(q):
                      [txz - twy, tyz + twx, one - (txx + tyy)]], f32)
 
 
-def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl):
-    """A, b (float32), n_valid, sum_r2 for one sweep; vectorised float32 numpy, sums by fsum."""
+def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights=False):
+    """A, b (float32), n_valid, sum_r2 [, weighted error sum] for one sweep; vectorised float32
+    numpy, sums by fsum.  weight_fn(residuals f32) -> weights f32 (Tracker.cpp:496)."""
     fx, fy, cx, cy = (f32(K[k][lvl]) for k in ("fx", "fy", "cx", "cy"))
     ifx, ify = f32(K["invfx"][lvl]), f32(K["invfy"][lvl])
     rows, cols = I2.shape
@@ -143,23 +165,43 @@ def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl):
         b = Jw1[c].astype(np.float64) if Jw1[c] is not None else 0.0
         J[:, c] = (jx * a + jy * b).astype(f32).astype(np.float64)
     r50 = (r.astype(f32) * f32(50)).astype(np.float64)
+    esum = None
+    if weight_fn is not None:
+        rf = r.astype(f32)
+        wgt = weight_fn(rf).astype(f32)
+        esum = math.fsum(rf.astype(np.float64) * (rf * wgt).astype(np.float64))  # Tracker.cpp:500
+        sc = np.sqrt(wgt).astype(f32) if sqrt_weights else wgt
+        J = (sc[:, None] * J.astype(f32)).astype(f32).astype(np.float64)    # Tracker.cpp:554-557
+        r50 = ((rf * f32(50)) * sc).astype(f32).astype(np.float64)          # Tracker.cpp:559,562
     A = np.zeros((6, 6), f32)
     b = np.zeros(6, f32)
     for i in range(6):
         for j in range(i, 6):
             A[i, j] = A[j, i] = f32(math.fsum(J[:, i] * J[:, j]))   # exactly rounded sums
         b[i] = f32(-math.fsum(J[:, i] * r50))
+    if weight_fn is not None:
+        return A, b, int(valid.sum()), int((r * r).sum()), esum
     return A, b, int(valid.sum()), int((r * r).sum())
 
 
-@pytest.mark.parametrize("calib,seed", [("small", 0), ("tum", 2)])
-def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed):
+@pytest.mark.parametrize("calib,seed,mode", [("small", 0, 0), ("tum", 2, 0), ("small", 1, 1),
+                                             ("tum", 2, 1), ("small", 1, 2)])
+def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed, mode):
     cv2 = pytest.importorskip("cv2")
     w, h, fx, fy, cx, cy = synth.CALIB[calib]
     prev, cur, _, _ = synth.render_pair(calib, seed)
     fp, fc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
-    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=7.5)
     _, _, tr = oracle.estimate_pose(p, fp, fc)
+    weight_fn = None
+    if mode == 1:   # Tukey / MAD evaluated with the real OpenCV (tests/test_oracle_vs_cv2.py)
+        from test_oracle_vs_cv2 import cv_tukey
+        weight_fn = lambda r: cv_tukey(r)[0]
+    elif mode == 2:
+        def weight_fn(r):
+            a = np.abs(r)
+            with np.errstate(divide="ignore"):
+                return np.where(a <= f32(7.5), f32(1), f32(7.5) / a).astype(f32)
     K = oracle.init_pyramid(w, h, fx, fy, cx, cy, 5)
     pose = np.array([0, 0, 0, 1, 0, 0, 0], f32)
     checked = 0
@@ -167,10 +209,11 @@ def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed):
         if t.k == 0 and i > 0:  # new level: previous pose went through the level transition
             pose = oracle.se3_scale_level(pose)
         lvl = t.level
-        A, b, nv, sr2 = np_iteration(fp.cand[lvl], fp.images[lvl], fc.images[lvl], fp.gx[lvl],
-                                     fp.gy[lvl], pose, K, lvl)
+        res = np_iteration(fp.cand[lvl], fp.images[lvl], fc.images[lvl], fp.gx[lvl],
+                           fp.gy[lvl], pose, K, lvl, weight_fn, sqrt_weights=(mode == 2))
+        A, b, nv, sr2 = res[:4]
         assert (nv, sr2) == (t.n_valid, t.sum_r2), (lvl, t.k)
-        err = f32(np.float64(f32(1.0 / nv)) * np.float64(sr2))
+        err = f32(np.float64(f32(1.0 / nv)) * np.float64(sr2 if mode == 0 else res[4]))
         assert err == f32(t.error)
         if not t.broke:
             assert np.array_equal(A, np.array(t.A[:], f32).reshape(6, 6)), (lvl, t.k)

@@ -164,3 +164,69 @@ def test_init_pyramid_matches_source_formulas(oracle):
             assert K["fx"][l] == efx and K["cx"][l] == ecx
             assert K["invfx"][l] == f(1) / efx
             assert K["w"][l] == w >> l and K["h"][l] == h >> l
+
+
+# ---- robust weights (Tracker.cpp:1571-1594, 1607-1654) --------------
+def cv_median_mat(v):
+    """Tracker::MedianMat with the real OpenCV: convertTo(CV_8UC1) + calcHist + the loop."""
+    v = np.asarray(v, np.float32).reshape(-1, 1)
+    # Mat::convertTo(CV_8UC1) == saturate_cast<uchar>(cvRound(x)); cv2.add with dtype runs the
+    # same saturating conversion kernel
+    ch = cv2.add(v, np.zeros_like(v), dtype=cv2.CV_8U)
+    hist = cv2.calcHist([ch], [0], None, [256], [0, 256])
+    m = np.float32((ch.shape[0] * ch.shape[1]) // 2)
+    bin_, med = 0, -1.0
+    for i in range(256):
+        if med >= 0.0:
+            break
+        bin_ += int(np.rint(hist[i, 0]))
+        if np.float32(bin_) > m and med < 0.0:
+            med = float(i)
+    return med
+
+
+def cv_tukey(v):
+    v = np.asarray(v, np.float32)
+    med = np.float32(cv_median_mat(v))
+    dev = cv2.absdiff(v.reshape(-1, 1), np.full((v.size, 1), med, np.float32)).ravel()
+    MAD = raw_mad = np.float32(1.4826) * np.float32(cv_median_mat(dev))
+    if MAD == 0:
+        MAD = np.float32(1)
+    b = np.float32(4.6851)
+    inv_MAD = np.float32(1.0 / np.float64(MAD))
+    inv_b2 = np.float32(1.0 / np.float64(b * b))
+    x = v * inv_MAD
+    t = (1.0 - ((x * x) * inv_b2).astype(np.float64)).astype(np.float32)
+    return np.where(np.abs(x) <= b, t * t, np.float32(0)).astype(np.float32), raw_mad
+
+
+@pytest.mark.parametrize("scale", [0.0, 1.0, 4.0, 25.0, 90.0, 300.0])
+def test_median_mad_tukey_match_cv(oracle, scale):
+    rng = np.random.default_rng(int(scale * 10) + 1)
+    for trial in range(12):
+        n = int(rng.integers(1, 6000))
+        v = np.clip(np.rint(rng.normal(rng.normal(0, 3), scale, n)), -255, 255).astype(np.float32)
+        if trial == 0:
+            v[:] = 3.0  # MAD == 0 -> replaced by 1 (Tracker.cpp:1634-1637)
+        assert oracle.median_mat(v) == cv_median_mat(v)
+        w_ref, mad_ref = cv_tukey(v)
+        assert np.float32(oracle.mad(v)) == mad_ref
+        assert np.array_equal(oracle.tukey_weights(v), w_ref)
+
+
+def test_median_mat_saturation_and_ties(oracle):
+    # negatives clamp to 0, .5 rounds to even, > 255 clamps (saturate_cast<uchar>(cvRound))
+    v = np.array([-7, -0.5, 0.5, 1.5, 2.5, 254.5, 255.5, 400], np.float32)
+    assert oracle.median_mat(v) == cv_median_mat(v)
+    for n in (1, 2, 3, 4, 5, 8, 9):
+        v = np.arange(n, dtype=np.float32) * 3
+        assert oracle.median_mat(v) == cv_median_mat(v)
+
+
+def test_huber_weights(oracle):
+    v = np.arange(-255, 256, dtype=np.float32)
+    for d in (0.5, 7.5, 10.0, 300.0):
+        a = np.abs(v)
+        with np.errstate(divide="ignore"):
+            ref = np.where(a <= np.float32(d), np.float32(1), np.float32(d) / a).astype(np.float32)
+        assert np.array_equal(oracle.huber_weights(v, d), ref)

@@ -12,6 +12,7 @@ OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
 SOLVE_LU, SOLVE_INVERSE = 0, 1
 FLAG_TRACE = 1
 FLAG_DMMA_ACCUM = 2
+WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 
 
@@ -23,6 +24,7 @@ class Config(C.Structure):
         ("max_iterations", C.c_int), ("epsilon", C.c_float), ("residual_scale", C.c_float),
         ("gradient_threshold", C.c_double), ("solve_mode", C.c_int), ("device", C.c_int),
         ("max_frames", C.c_int), ("cluster_size", C.c_int), ("flags", C.c_uint),
+        ("weight_mode", C.c_int), ("huber_delta", C.c_float),
     ]
 
 

@@ -156,6 +156,8 @@ int build_geom(const uwt_config& c, Geom& g) {
   g.residual_scale = c.residual_scale;
   g.gradient_threshold = c.gradient_threshold;
   g.solve_mode = c.solve_mode;
+  g.weight_mode = c.weight_mode;
+  g.huber_delta = c.huber_delta;
   size_t plane = 0, cand = 0, rec = 0, cnt = 0;
   int tiles = 0, items = 0;
   // Tracker::InitializePyramid, Tracker.cpp:297-340 (same expression types as the source:
@@ -311,6 +313,8 @@ int uwt_default_config(uwt_config* cfg) {
   cfg->max_frames = 2;
   cfg->cluster_size = 0;
   cfg->flags = 0;
+  cfg->weight_mode = UWT_WEIGHT_IDENTITY;  // Tracker.cpp:495
+  cfg->huber_delta = 10.0f;
   return UWT_OK;
 }
 
@@ -339,6 +343,12 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
     return fail(nullptr, UWT_E_INVALID, "max_iterations and max_frames must be >= 1");
   if (c.solve_mode != UWT_SOLVE_LU && c.solve_mode != UWT_SOLVE_INVERSE)
     return fail(nullptr, UWT_E_INVALID, "bad solve_mode %d", c.solve_mode);
+  if (c.weight_mode < UWT_WEIGHT_IDENTITY || c.weight_mode > UWT_WEIGHT_HUBER)
+    return fail(nullptr, UWT_E_INVALID, "bad weight_mode %d", c.weight_mode);
+  if (c.weight_mode == UWT_WEIGHT_HUBER && !(c.huber_delta > 0.0f))
+    return fail(nullptr, UWT_E_INVALID, "huber_delta must be > 0");
+  if (c.weight_mode != UWT_WEIGHT_IDENTITY && (c.flags & UWT_FLAG_DMMA_ACCUM))
+    return fail(nullptr, UWT_E_INVALID, "UWT_FLAG_DMMA_ACCUM supports identity weights only");
   if (c.cluster_size != 0 && c.cluster_size != 1 && c.cluster_size != 2 && c.cluster_size != 4 &&
       c.cluster_size != 8 && c.cluster_size != 16)
     return fail(nullptr, UWT_E_INVALID, "cluster_size must be 0, 1, 2, 4, 8 or 16");
@@ -545,7 +555,11 @@ int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* ho
     // it has finished
     if (t->stage_busy[sb]) UWT_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->stage_free[sb], 0));
     uint8_t* stage = t->d_stage[sb];
-    if (frame_stride == row_stride * h) {
+    if (row_stride == w && frame_stride == w * h) {
+      // densely packed frames: one linear copy (largest DMA descriptors)
+      UWT_CUDA(t, cudaMemcpyAsync(stage, src, w * h * cnt, cudaMemcpyHostToDevice,
+                                  t->copy_stream));
+    } else if (frame_stride == row_stride * h) {
       // frames are contiguous: one strided copy for the whole chunk
       UWT_CUDA(t, cudaMemcpy2DAsync(stage, w, src, row_stride, w, h * cnt,
                                     cudaMemcpyHostToDevice, t->copy_stream));
@@ -651,6 +665,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   {
     const LevelGeom& Lf = t->geom.lv[t->cfg.last_level];
     if (n == 1 && t->cfg.cluster_size == 0 && !(t->cfg.flags & UWT_FLAG_TRACE) &&
+        t->cfg.weight_mode == UWT_WEIGHT_IDENTITY &&
         (long long)Lf.w * Lf.h >= (1 << 20)) {
       ShardState s;
       std::memset(&s, 0, sizeof(s));
@@ -760,6 +775,8 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
   if ((rc = check_slots(t, 1, &cur_slot))) return rc;
   if (nranks < 1 || rank < 0 || rank >= nranks)
     return fail(t, UWT_E_INVALID, "bad shard rank %d of %d", rank, nranks);
+  if (t->cfg.weight_mode != UWT_WEIGHT_IDENTITY)
+    return fail(t, UWT_E_INVALID, "the sharded mode supports identity weights only");
   if (!t->slots[prev_slot].candidates)
     return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slot);
   if (!t->slots[cur_slot].pyramid) return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slot);

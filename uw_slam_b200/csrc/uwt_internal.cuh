@@ -45,6 +45,8 @@ struct Geom {
   float epsilon, residual_scale;
   double gradient_threshold;
   int solve_mode;
+  int weight_mode;    // UWT_WEIGHT_*
+  float huber_delta;
   // per-slot strides (elements)
   size_t plane_elems, cand_elems, rec_elems, cnt_elems, tile_elems;
   int grad_tiles_total;  // gradient tiles per slot over all levels
