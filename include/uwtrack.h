@@ -16,6 +16,11 @@
  *   Tracker::ObtainCandidatePoints(F*)  include/Tracker.h:145   uwt_select_candidates
  *   Tracker::EstimatePose(F*,F*)        include/Tracker.h:122   uwt_estimate_pose
  *   Tracker::WarpFunction(Mat,SE3,int)  include/Tracker.h:193   uwt_warp_points
+ *   CameraModel::GetCameraModel (rectify) src/CameraModel.cpp:84 uwt_camera_optimal_matrix,
+ *                                                               uwt_camera_undistort_maps
+ *   CameraModel::Undistort              src/CameraModel.cpp:101 uwt_undistort_image
+ *   System::CalculateROI                src/System.cpp:148      uwt_calculate_roi
+ *   System::AddFrame remap + ROI crop   src/System.cpp:232-235  uwt_set_undistortion
  *   uw::Frame members (images_, gradientX_, gradientY_,        uwt_get_image, uwt_get_gradients,
  *     gradient_, candidatePoints_)      include/System.h:63-103 uwt_get_candidates
  *
@@ -134,6 +139,34 @@ int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* ho
 /* Same, from frames already resident in DEVICE memory. */
 int uwt_set_frames_device(uwt_tracker* t, int n, const int* slots, const uint8_t* dev,
                           size_t row_stride, size_t frame_stride);
+/* ---- calibration / undistortion front-end ----
+ * CameraModel::GetCameraModel, rectify branch (src/CameraModel.cpp:84-98): the two one-off
+ * OpenCV calls, on the host (K9 / newK9: row-major 3x3 CV_32F like the reference's Mats;
+ * dist4 = k1 k2 p1 p2 of calibration/<name>.xml <rectification>; results follow OpenCV 4.x):
+ *   getOptimalNewCameraMatrix(K, dist, in_size, alpha, out_size, nullptr, false)
+ *   initUndistortRectifyMap(K, dist, Mat(), newK, out_size, CV_16SC2, map1, map2)
+ * map1: out_h*out_w*2 int16 (integer source x, y); map2: out_h*out_w uint16 ((fy<<5)|fx). */
+int uwt_camera_optimal_matrix(const float* K9, const float* dist4, int in_w, int in_h,
+                              double alpha, int out_w, int out_h, float* newK9);
+int uwt_camera_undistort_maps(const float* K9, const float* dist4, const float* newK9, int out_w,
+                              int out_h, int16_t* map1, uint16_t* map2);
+/* CameraModel::Undistort (src/CameraModel.cpp:101-103): cv::remap(INTER_LINEAR, fixed-point
+ * maps, constant border 0) of ONE host image on `device`; no handle needed (used once, for the
+ * ROI search below, before the tracker size is known). */
+int uwt_undistort_image(int device, const uint8_t* src, int in_w, int in_h, size_t src_stride,
+                        const int16_t* map1, const uint16_t* map2, int out_w, int out_h,
+                        uint8_t* dst);
+/* System::CalculateROI (src/System.cpp:148-191) on the first undistorted image (host):
+ * roi4 = x, y of the top-left corner and the new w_, h_. */
+int uwt_calculate_roi(const uint8_t* undistorted, int w, int h, size_t stride, int* roi4);
+/* System::AddFrame, `remap(...); images_[0] = distortion(ROI)` (src/System.cpp:232-235): after
+ * this call uwt_upload_frames / uwt_set_frames_device take the DISTORTED in_w x in_h frames;
+ * the remap and the crop at (roi_x, roi_y) are fused into the level-0 load of the pyramid
+ * kernel.  The maps are map_w x map_h (the reference's out_width x out_height); the handle's
+ * width x height is the cropped size.  map1 == map2 == NULL switches undistortion off. */
+int uwt_set_undistortion(uwt_tracker* t, const int16_t* map1, const uint16_t* map2, int map_w,
+                         int map_h, int in_w, int in_h, int roi_x, int roi_y);
+
 /* Tracker::ApplyGradient for n slots: gradient_ (u8) on every pyramid level.  The int16
  * gradientX_ / gradientY_ values reach the tracker through the packed candidate records; the
  * full planes are produced on demand by uwt_get_gradients (same stencil, same integers). */

@@ -20,8 +20,10 @@
  */
 #include "uw_oracle.h"
 
+#include <cfloat>
 #include <chrono>
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -485,6 +487,146 @@ int uwo_lu_invert6(const float* A36, float* Ainv36) {
   }
   std::memcpy(Ainv36, B, sizeof(B));
   return 1;
+}
+
+// ---- calibration / undistortion front-end (CameraModel.cpp:84-103, System.cpp:148-191, 232-239)
+// cv::undistortPoints on one pixel point with P = R = identity, 5 fixed-point iterations
+// (OpenCV 4.x cvUndistortPointsInternal with the (ITER, 5) criteria used by
+// getOptimalNewCameraMatrix); k = k1 k2 p1 p2, all higher coefficients zero.
+static void undistort_point_normalized(double u, double v, double fx, double fy, double cx,
+                                       double cy, const double* k, double* xo, double* yo) {
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double x = (u - cx) * ifx, y = (v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((0. * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) {
+      x = (u - cx) * ifx;
+      y = (v - cy) * ify;
+      break;
+    }
+    const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+    const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + 0. * r2 + 0. * r2 * r2;
+    x = (x0 - deltaX) * icdist;
+    y = (y0 - deltaY) * icdist;
+  }
+  *xo = x;
+  *yo = y;
+}
+
+void uwo_optimal_new_camera_matrix(const float* K9, const float* dist4, int in_w, int in_h,
+                                   double alpha, int out_w, int out_h, float* newK9) {
+  // getUndistortRectangles: 9 x 9 grid of image points -> normalised undistorted coordinates
+  const int N = 9;
+  const double k[4] = {dist4[0], dist4[1], dist4[2], dist4[3]};
+  double iX0 = -FLT_MAX, iX1 = FLT_MAX, iY0 = -FLT_MAX, iY1 = FLT_MAX;
+  double oX0 = FLT_MAX, oX1 = -FLT_MAX, oY0 = FLT_MAX, oY1 = -FLT_MAX;
+  for (int y = 0; y < N; ++y)
+    for (int x = 0; x < N; ++x) {
+      double px, py;
+      undistort_point_normalized((double)x * (in_w - 1) / (N - 1), (double)y * (in_h - 1) / (N - 1),
+                                 K9[0], K9[4], K9[2], K9[5], k, &px, &py);
+      oX0 = std::min(oX0, px); oX1 = std::max(oX1, px);
+      oY0 = std::min(oY0, py); oY1 = std::max(oY1, py);
+      if (x == 0) iX0 = std::max(iX0, px);
+      if (x == N - 1) iX1 = std::min(iX1, px);
+      if (y == 0) iY0 = std::max(iY0, py);
+      if (y == N - 1) iY1 = std::min(iY1, py);
+    }
+  const double iw = iX1 - iX0, ih = iY1 - iY0, ow = oX1 - oX0, oh = oY1 - oY0;
+  // projections mapping the inner / outer rectangle to the viewport, blended by alpha
+  const double fx0 = (out_w - 1) / iw, fy0 = (out_h - 1) / ih;
+  const double cx0 = -fx0 * iX0, cy0 = -fy0 * iY0;
+  const double fx1 = (out_w - 1) / ow, fy1 = (out_h - 1) / oh;
+  const double cx1 = -fx1 * oX0, cy1 = -fy1 * oY0;
+  double M[9];
+  for (int i = 0; i < 9; ++i) M[i] = K9[i];
+  M[0] = fx0 * (1 - alpha) + fx1 * alpha;
+  M[4] = fy0 * (1 - alpha) + fy1 * alpha;
+  M[2] = cx0 * (1 - alpha) + cx1 * alpha;
+  M[5] = cy0 * (1 - alpha) + cy1 * alpha;
+  for (int i = 0; i < 9; ++i) newK9[i] = (float)M[i];
+}
+
+void uwo_init_undistort_rectify_map(const float* K9, const float* dist4, const float* newK9,
+                                    int out_w, int out_h, int16_t* map1, uint16_t* map2) {
+  // iR = (newK * I)^-1 : cv::invert of a 3 x 3 CV_64F matrix uses the cofactor formula
+  double S[9], ir[9];
+  for (int i = 0; i < 9; ++i) S[i] = newK9[i];
+  double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) +
+             S[2] * (S[3] * S[7] - S[4] * S[6]);
+  if (d != 0.) {
+    d = 1. / d;
+    ir[0] = (S[4] * S[8] - S[5] * S[7]) * d;
+    ir[1] = (S[2] * S[7] - S[1] * S[8]) * d;
+    ir[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+    ir[3] = (S[5] * S[6] - S[3] * S[8]) * d;
+    ir[4] = (S[0] * S[8] - S[2] * S[6]) * d;
+    ir[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+    ir[6] = (S[3] * S[7] - S[4] * S[6]) * d;
+    ir[7] = (S[1] * S[6] - S[0] * S[7]) * d;
+    ir[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+  } else {
+    for (int i = 0; i < 9; ++i) ir[i] = 0.;
+  }
+  const double u0 = K9[2], v0 = K9[5], fx = K9[0], fy = K9[4];
+  const double k1 = dist4[0], k2 = dist4[1], p1 = dist4[2], p2 = dist4[3];
+  for (int i = 0; i < out_h; ++i) {
+    double _x = i * ir[1] + ir[2], _y = i * ir[4] + ir[5], _w = i * ir[7] + ir[8];
+    for (int j = 0; j < out_w; ++j, _x += ir[0], _y += ir[3], _w += ir[6]) {
+      const double w = 1. / _w, x = _x * w, y = _y * w;
+      const double x2 = x * x, y2 = y * y;
+      const double r2 = x2 + y2, _2xy = 2 * x * y;
+      const double kr = (1 + ((0. * r2 + k2) * r2 + k1) * r2) / (1 + ((0. * r2 + 0.) * r2 + 0.) * r2);
+      const double xd = (x * kr + p1 * _2xy + p2 * (r2 + 2 * x2) + 0. * r2 + 0. * r2 * r2);
+      const double yd = (y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy + 0. * r2 + 0. * r2 * r2);
+      const double u = fx * xd + u0, v = fy * yd + v0;
+      // saturate_cast<int>(u * INTER_TAB_SIZE): cvRound
+      const int iu = (int)std::nearbyint(u * 32), iv = (int)std::nearbyint(v * 32);
+      const int sx = iu >> 5, sy = iv >> 5;
+      map1[((size_t)i * out_w + j) * 2 + 0] =
+          (int16_t)(sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx));
+      map1[((size_t)i * out_w + j) * 2 + 1] =
+          (int16_t)(sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy));
+      map2[(size_t)i * out_w + j] = (uint16_t)((iv & 31) * 32 + (iu & 31));
+    }
+  }
+}
+
+void uwo_remap_bilinear(const uint8_t* src, int sw, int sh, const int16_t* map1,
+                        const uint16_t* map2, int dw, int dh, uint8_t* dst) {
+  // remapBilinear<FixedPtCast<int, uchar, 15>>: integer weights (32-a)(32-b)*32 out of 2^15,
+  // samples outside the image read the constant border value 0
+  for (int y = 0; y < dh; ++y)
+    for (int x = 0; x < dw; ++x) {
+      const int sx = map1[((size_t)y * dw + x) * 2], sy = map1[((size_t)y * dw + x) * 2 + 1];
+      const int f = map2[(size_t)y * dw + x] & 1023;
+      const int a = f & 31, b = f >> 5;
+      auto S = [&](int yy, int xx) -> int {
+        return (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sw + xx] : 0;
+      };
+      const int v = S(sy, sx) * ((32 - a) * (32 - b) * 32) + S(sy, sx + 1) * (a * (32 - b) * 32) +
+                    S(sy + 1, sx) * ((32 - a) * b * 32) + S(sy + 1, sx + 1) * (a * b * 32);
+      const int o = (v + (1 << 14)) >> 15;
+      dst[(size_t)y * dw + x] = (uint8_t)(o < 0 ? 0 : (o > 255 ? 255 : o));
+    }
+}
+
+int uwo_calculate_roi(const uint8_t* und, int w, int h, int* roi4) {
+  // System.cpp:155-190
+  const int x_middle = (int)((w - 1) * 0.5), y_middle = (int)((h - 1) * 0.5);
+  int p1x = 0, p1y = 0, p2x = w - 1, p2y = h - 1;
+  while (und[(size_t)y_middle * w + p1x] == 0) if (++p1x >= w) return -1;
+  while (und[(size_t)y_middle * w + p2x] == 0) if (--p2x < 0) return -1;
+  while (und[(size_t)p1y * w + x_middle] == 0) if (++p1y >= h) return -1;
+  while (und[(size_t)p2y * w + x_middle] == 0) if (--p2y < 0) return -1;
+  p1x += 5; p2x -= 5; p1y += 5; p2y -= 5;  // error margin
+  roi4[0] = p1x;
+  roi4[1] = p1y;
+  roi4[2] = p2x - p1x;  // w_ = p2.x - p1.x, also Rect(p1, p2).width
+  roi4[3] = p2y - p1y;
+  return 0;
 }
 
 float uwo_median_mat(const float* v, int n) { return median_mat(v, n); }

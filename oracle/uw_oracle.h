@@ -115,6 +115,26 @@ void uwo_huber_weights(const float* v, int n, float delta, float* w);
 int uwo_lu_solve6(const float* A36, const float* b6, float* x6);
 int uwo_lu_invert6(const float* A36, float* Ainv36);
 
+/* ---- calibration / undistortion front-end ----------------------------
+ * CameraModel::GetCameraModel rectify branch (CameraModel.cpp:84-98): the OpenCV calls it makes,
+ * restated after OpenCV 4.x (the version that can be pinned here, cv2 4.13). */
+/* cv::getOptimalNewCameraMatrix(K, dist(k1 k2 p1 p2), in_size, alpha, out_size, 0, false).
+ * K, newK: row-major 3x3 float (CV_32F like the reference's Mats). */
+void uwo_optimal_new_camera_matrix(const float* K9, const float* dist4, int in_w, int in_h,
+                                   double alpha, int out_w, int out_h, float* newK9);
+/* cv::initUndistortRectifyMap(K, dist, Mat(), newK, out_size, CV_16SC2, map1, map2):
+ * map1 = out_h x out_w x 2 int16 (integer source x, y), map2 = out_h x out_w uint16
+ * (5-bit fractions: (fy << 5) | fx). */
+void uwo_init_undistort_rectify_map(const float* K9, const float* dist4, const float* newK9,
+                                    int out_w, int out_h, int16_t* map1, uint16_t* map2);
+/* cv::remap(src, dst, map1, map2, INTER_LINEAR) for 8-bit images with fixed-point maps
+ * (BORDER_CONSTANT 0), CameraModel.cpp:101-103 / System.cpp:232-234. */
+void uwo_remap_bilinear(const uint8_t* src, int sw, int sh, const int16_t* map1,
+                        const uint16_t* map2, int dw, int dh, uint8_t* dst);
+/* System::CalculateROI (System.cpp:148-191) on the first undistorted image: roi4 = x, y of the
+ * top-left corner and the new w_, h_ (p2 - p1).  Returns 0, or -1 if a scan leaves the image. */
+int uwo_calculate_roi(const uint8_t* undistorted, int w, int h, int* roi4);
+
 /* Whole-frame preprocessing into caller-provided per-level arrays.
  * images[l]: u8 w_l*h_l (level 0 is input, 1.. are written). */
 void uwo_build_pyramid(const uwo_params* p, uint8_t* const* images);

@@ -131,6 +131,61 @@ def huber_weights(v, delta):
     return w
 
 
+def optimal_new_camera_matrix(K, dist, in_size, alpha, out_size):
+    K = np.ascontiguousarray(K, np.float32)
+    d = np.ascontiguousarray(dist, np.float32).ravel()
+    o = np.empty((3, 3), np.float32)
+    f = lib().uwo_optimal_new_camera_matrix
+    f.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                                C.POINTER(C.c_float)]
+    f.restype = None
+    f(_p(K, C.c_float), _p(d, C.c_float), in_size[0], in_size[1], float(alpha), out_size[0],
+      out_size[1], _p(o, C.c_float))
+    return o
+
+
+def init_undistort_rectify_map(K, dist, newK, out_size):
+    K = np.ascontiguousarray(K, np.float32)
+    d = np.ascontiguousarray(dist, np.float32).ravel()
+    nK = np.ascontiguousarray(newK, np.float32)
+    w, h = out_size
+    m1 = np.empty((h, w, 2), np.int16)
+    m2 = np.empty((h, w), np.uint16)
+    f = lib().uwo_init_undistort_rectify_map
+    f.argtypes = [C.POINTER(C.c_float)] * 3 + [C.c_int, C.c_int, C.POINTER(C.c_int16),
+                                                C.POINTER(C.c_uint16)]
+    f.restype = None
+    f(_p(K, C.c_float), _p(d, C.c_float), _p(nK, C.c_float), w, h, _p(m1, C.c_int16),
+      _p(m2, C.c_uint16))
+    return m1, m2
+
+
+def remap_bilinear(src, map1, map2):
+    src = np.ascontiguousarray(src, np.uint8)
+    m1 = np.ascontiguousarray(map1, np.int16)
+    m2 = np.ascontiguousarray(map2, np.uint16)
+    h, w = m2.shape
+    out = np.empty((h, w), np.uint8)
+    f = lib().uwo_remap_bilinear
+    f.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_int16),
+                  C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    f.restype = None
+    f(_p(src, C.c_uint8), src.shape[1], src.shape[0], _p(m1, C.c_int16), _p(m2, C.c_uint16), w, h,
+      _p(out, C.c_uint8))
+    return out
+
+
+def calculate_roi(undistorted):
+    u = np.ascontiguousarray(undistorted, np.uint8)
+    roi = (C.c_int * 4)()
+    f = lib().uwo_calculate_roi
+    f.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    f.restype = C.c_int
+    if f(_p(u, C.c_uint8), u.shape[1], u.shape[0], roi) != 0:
+        raise RuntimeError("CalculateROI scanned past the image border")
+    return tuple(roi)
+
+
 def pyr_down(img):
     h, w = img.shape
     img = np.ascontiguousarray(img, np.uint8)

@@ -4,5 +4,6 @@ The compute lives in libuwtrack.so (hand-written CUDA for sm_100a behind the C A
 include/uwtrack.h); this package is the thin host-side mirror of the reference's
 Tracker / CameraModel / Frame surface plus the synthetic-input generator.
 """
-from .tracker import CameraModel, Frame, Tracker, UwtError  # noqa: F401
+from .tracker import (AlignROI, CalculateROI, CameraModel, Frame, Tracker,  # noqa: F401
+                      UwtError)
 from . import synth  # noqa: F401

@@ -64,6 +64,15 @@ SIGNATURES = {
     "uwt_synchronize": (C.c_int, [_H]),
     "uwt_upload_frames": (C.c_int, [_H, C.c_int, _ip, C.c_void_p, C.c_size_t, C.c_size_t]),
     "uwt_set_frames_device": (C.c_int, [_H, C.c_int, _ip, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "uwt_camera_optimal_matrix": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_double, C.c_int,
+                                            C.c_int, _fp]),
+    "uwt_camera_undistort_maps": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _i16p,
+                                            C.POINTER(C.c_uint16)]),
+    "uwt_undistort_image": (C.c_int, [C.c_int, _u8p, C.c_int, C.c_int, C.c_size_t, _i16p,
+                                      C.POINTER(C.c_uint16), C.c_int, C.c_int, _u8p]),
+    "uwt_calculate_roi": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_size_t, _ip]),
+    "uwt_set_undistortion": (C.c_int, [_H, _i16p, C.POINTER(C.c_uint16), C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int]),
     "uwt_apply_gradient": (C.c_int, [_H, C.c_int, _ip]),
     "uwt_select_candidates": (C.c_int, [_H, C.c_int, _ip]),
     "uwt_estimate_pose": (C.c_int, [_H, C.c_int, _ip, _ip, _fp, _fp, C.POINTER(TrackStats)]),

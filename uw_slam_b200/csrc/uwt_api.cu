@@ -58,6 +58,10 @@ struct uwt_tracker {
   int stage_next = 0;
   size_t stage_frames = 0;
   cudaEvent_t poses_ready = nullptr;  // recorded after the D2H of the last estimate
+  // undistortion front-end (uwt_set_undistortion): device copies of the fixed-point maps
+  RemapArgs remap;
+  short2* d_map1 = nullptr;
+  uint16_t* d_map2 = nullptr;
   // sharded single-frame mode
   ShardState* d_shard = nullptr;
   double* d_shard_partials = nullptr;
@@ -267,6 +271,8 @@ void destroy_impl(uwt_tracker* t) {
     if (t->stage_free[i]) cudaEventDestroy(t->stage_free[i]);
   }
   if (t->poses_ready) cudaEventDestroy(t->poses_ready);
+  cudaFree(t->d_map1);
+  cudaFree(t->d_map2);
   for (void* p : t->ipc_opened)
     if (p) cudaIpcCloseMemHandle(p);
   cudaFree(t->d_fused);
@@ -523,7 +529,7 @@ static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t
   if (rc) return rc;
   ProfSpan span(t, UWT_K_PYRAMID);
   const int k = launch_pyramid(t->geom, t->pools, n, r->d_int, dev_src, row_stride, frame_stride,
-                               false, t->stream);
+                               false, t->stream, t->remap);
   span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "pyramid kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
@@ -542,10 +548,12 @@ int uwt_upload_frames(uwt_tracker* t, int n, const int* slots, const uint8_t* ho
                       size_t row_stride, size_t frame_stride) {
   int rc = check_slots(t, n, slots);
   if (rc) return rc;
-  if (!host || row_stride < (size_t)t->cfg.width)
-    return fail(t, UWT_E_INVALID, "host NULL or row_stride < width");
+  // with undistortion enabled the caller hands over DISTORTED in_w x in_h frames
+  const size_t w = t->remap.map1 ? t->remap.in_w : t->cfg.width;
+  const size_t h = t->remap.map1 ? t->remap.in_h : t->cfg.height;
+  if (!host || row_stride < w)
+    return fail(t, UWT_E_INVALID, "host NULL or row_stride < source width %zu", w);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  const size_t w = t->cfg.width, h = t->cfg.height;
   for (size_t done = 0; done < (size_t)n;) {
     const size_t cnt = std::min(t->stage_frames, (size_t)n - done);
     const uint8_t* src = host + done * frame_stride;
@@ -583,10 +591,58 @@ int uwt_set_frames_device(uwt_tracker* t, int n, const int* slots, const uint8_t
                           size_t row_stride, size_t frame_stride) {
   int rc = check_slots(t, n, slots);
   if (rc) return rc;
-  if (!dev || row_stride < (size_t)t->cfg.width)
-    return fail(t, UWT_E_INVALID, "dev NULL or row_stride < width");
+  if (!dev || row_stride < (size_t)(t->remap.map1 ? t->remap.in_w : t->cfg.width))
+    return fail(t, UWT_E_INVALID, "dev NULL or row_stride < source width");
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   return pyramid_common(t, n, slots, dev, row_stride, frame_stride);
+}
+
+int uwt_set_undistortion(uwt_tracker* t, const int16_t* map1, const uint16_t* map2, int map_w,
+                         int map_h, int in_w, int in_h, int roi_x, int roi_y) {
+  if (!t) return UWT_E_INVALID;
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  // frames in flight still use the current maps / staging buffers
+  UWT_CUDA(t, cudaStreamSynchronize(t->copy_stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  const bool enable = map1 && map2;
+  size_t frame_bytes = (size_t)t->cfg.width * t->cfg.height;
+  if (enable) {
+    if (map_w < 1 || map_h < 1 || in_w < 1 || in_h < 1 || roi_x < 0 || roi_y < 0 ||
+        roi_x + t->cfg.width > map_w || roi_y + t->cfg.height > map_h)
+      return fail(t, UWT_E_INVALID,
+                  "ROI %dx%d at (%d,%d) does not fit the %dx%d undistortion maps", t->cfg.width,
+                  t->cfg.height, roi_x, roi_y, map_w, map_h);
+    frame_bytes = (size_t)in_w * in_h;
+  } else if (map1 || map2) {
+    return fail(t, UWT_E_INVALID, "map1 and map2 must both be given (or both NULL)");
+  }
+  cudaFree(t->d_map1);
+  cudaFree(t->d_map2);
+  t->d_map1 = nullptr;
+  t->d_map2 = nullptr;
+  t->remap = RemapArgs();
+  if (enable) {
+    const size_t n = (size_t)map_w * map_h;
+    UWT_CUDA(t, cudaMalloc(&t->d_map1, n * sizeof(short2)));
+    UWT_CUDA(t, cudaMalloc(&t->d_map2, n * sizeof(uint16_t)));
+    UWT_CUDA(t, cudaMemcpy(t->d_map1, map1, n * sizeof(short2), cudaMemcpyHostToDevice));
+    UWT_CUDA(t, cudaMemcpy(t->d_map2, map2, n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    t->remap.map1 = t->d_map1;
+    t->remap.map2 = t->d_map2;
+    t->remap.map_w = map_w; t->remap.map_h = map_h;
+    t->remap.in_w = in_w; t->remap.in_h = in_h;
+    t->remap.roi_x = roi_x; t->remap.roi_y = roi_y;
+  }
+  // staging buffers hold source frames: resize them for the (larger) distorted input
+  const size_t F = (size_t)t->cfg.max_frames;
+  t->stage_frames = std::max<size_t>(1, std::min<size_t>(F, ((size_t)256 << 20) / frame_bytes));
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(t->d_stage[i]);
+    t->d_stage[i] = nullptr;
+    t->stage_busy[i] = false;
+    UWT_CUDA(t, cudaMalloc(&t->d_stage[i], t->stage_frames * frame_bytes));
+  }
+  return UWT_OK;
 }
 
 int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {

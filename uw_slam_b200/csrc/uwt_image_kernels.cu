@@ -20,10 +20,30 @@ namespace uwt {
 // ----------------------------------------------------------------------------------------
 // K1: pyramid
 // ----------------------------------------------------------------------------------------
+// cv::remap(.., INTER_LINEAR) with fixed-point maps (CameraModel.cpp:101-103, System.cpp:232-234):
+// map1 = integer source (x, y), map2 = 5-bit fractions (fy << 5 | fx); integer weights
+// (32-a)(32-b)*32 of 2^15, rounded by (v + 2^14) >> 15; samples outside the source read the
+// constant border 0 (cv::BORDER_CONSTANT).  Bit-identical to OpenCV's remapBilinear for 8U.
+__device__ __forceinline__ uint32_t remap_pixel(const uint8_t* __restrict__ src, size_t row_stride,
+                                                int in_w, int in_h, short2 m, uint32_t frac) {
+  const int sx = m.x, sy = m.y;
+  const int a = frac & 31, b = (frac >> 5) & 31;
+  const bool x0 = sx >= 0 && sx < in_w, x1 = sx + 1 >= 0 && sx + 1 < in_w;
+  const bool y0 = sy >= 0 && sy < in_h, y1 = sy + 1 >= 0 && sy + 1 < in_h;
+  const uint8_t* p = src + (ptrdiff_t)sy * (ptrdiff_t)row_stride + sx;
+  const int v00 = (x0 && y0) ? __ldg(p) : 0;
+  const int v01 = (x1 && y0) ? __ldg(p + 1) : 0;
+  const int v10 = (x0 && y1) ? __ldg(p + row_stride) : 0;
+  const int v11 = (x1 && y1) ? __ldg(p + row_stride + 1) : 0;
+  const int v = v00 * ((32 - a) * (32 - b) * 32) + v01 * (a * (32 - b) * 32) +
+                v10 * ((32 - a) * b * 32) + v11 * (a * b * 32);
+  return (uint32_t)min(max((v + (1 << 14)) >> 15, 0), 255);
+}
+
 __global__ void __launch_bounds__(256)
 pyramid_kernel(const __grid_constant__ Geom geom, const Pools pools, const int* __restrict__ slots,
                const uint8_t* __restrict__ src, size_t row_stride, size_t frame_stride,
-               int src_is_slot, int src_aligned) {
+               int src_is_slot, int src_aligned, const RemapArgs rm) {
   __shared__ __align__(16) uint8_t s0[kPyrTile][kPyrTile];
   __shared__ __align__(16) uint8_t s1[32][32];
   __shared__ uint8_t s2[16][16];
@@ -37,8 +57,30 @@ pyramid_kernel(const __grid_constant__ Geom geom, const Pools pools, const int* 
   const LevelGeom& L0 = geom.lv[0];
   uint8_t* plane = pools.img + (size_t)slot * geom.plane_elems;
 
-  // ---- level 0 tile: 256 threads x 16 bytes ----
-  {
+  if (rm.map1) {
+    // ---- level 0 = remap + ROI crop of the distorted source frame (System.cpp:232-235) ----
+    // a warp walks 32 consecutive pixels of a row: map reads and source gathers stay coalesced
+    const uint8_t* frame = src + (size_t)blockIdx.z * frame_stride;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+      const int r = j * 4 + (t >> 6), c = t & 63;
+      const int gx = x0 + c, gy = y0 + r;
+      uint32_t v = 0;
+      if (gx < L0.w && gy < L0.h) {
+        const size_t mi = (size_t)(gy + rm.roi_y) * rm.map_w + (gx + rm.roi_x);
+        v = remap_pixel(frame, row_stride, rm.in_w, rm.in_h, __ldg(&rm.map1[mi]),
+                        __ldg(&rm.map2[mi]));
+      }
+      s0[r][c] = (uint8_t)v;
+    }
+    __syncthreads();
+    const int r = t >> 2, c = (t & 3) * 16;
+    const int gx = x0 + c, gy = y0 + r;
+    if (gx < L0.w && gy < L0.h)
+      *reinterpret_cast<uint4*>(plane + L0.plane_off + (size_t)gy * L0.pitch + gx) =
+          *reinterpret_cast<const uint4*>(&s0[r][c]);
+  } else {
+    // ---- level 0 tile: 256 threads x 16 bytes ----
     const int r = t >> 2, c = (t & 3) * 16;
     const int gx = x0 + c, gy = y0 + r;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -113,13 +155,32 @@ pyramid_kernel(const __grid_constant__ Geom geom, const Pools pools, const int* 
 }
 
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
-                   size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st) {
+                   size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st,
+                   const RemapArgs& rm) {
   const LevelGeom& L0 = g.lv[0];
   dim3 grid((L0.w + kPyrTile - 1) / kPyrTile, (L0.h + kPyrTile - 1) / kPyrTile, n);
   const int aligned =
       src_is_slot || ((((uintptr_t)src) | row_stride | frame_stride) & 15) == 0 ? 1 : 0;
   pyramid_kernel<<<grid, 256, 0, st>>>(g, p, d_slots, src, row_stride, frame_stride,
-                                       src_is_slot ? 1 : 0, aligned);
+                                       src_is_slot ? 1 : 0, aligned, rm);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// CameraModel::Undistort (CameraModel.cpp:101-103): plain remap of one image, no pyramid.
+__global__ void __launch_bounds__(256)
+remap_kernel(const uint8_t* __restrict__ src, size_t row_stride, int in_w, int in_h,
+             const short2* __restrict__ map1, const uint16_t* __restrict__ map2, int out_w,
+             int out_h, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= out_w || y >= out_h) return;
+  const size_t mi = (size_t)y * out_w + x;
+  dst[mi] = (uint8_t)remap_pixel(src, row_stride, in_w, in_h, __ldg(&map1[mi]), __ldg(&map2[mi]));
+}
+
+int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, const short2* map1,
+                 const uint16_t* map2, int out_w, int out_h, uint8_t* d_dst, cudaStream_t st) {
+  dim3 grid((out_w + 63) / 64, (out_h + 3) / 4);
+  remap_kernel<<<grid, 256, 0, st>>>(d_src, row_stride, in_w, in_h, map1, map2, out_w, out_h, d_dst);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -106,9 +106,22 @@ struct ShardFused {
   ShardMailbox* peer[kShardMaxRanks];  // peer[r] = rank r's mailbox as mapped in this process
 };
 
+// Undistortion front-end fused into the pyramid kernel's level-0 load (System.cpp:232-235):
+// fixed-point maps of cv::initUndistortRectifyMap(.., CV_16SC2, ..) in device memory.
+struct RemapArgs {
+  const short2* map1 = nullptr;    // [map_h][map_w] integer source (x, y); nullptr = no remap
+  const uint16_t* map2 = nullptr;  // [map_h][map_w] (fy << 5) | fx
+  int map_w = 0, map_h = 0;
+  int in_w = 0, in_h = 0;          // size of the distorted source frames
+  int roi_x = 0, roi_y = 0;        // top-left corner of the crop inside the maps
+};
+
 // kernel launchers (each returns the number of kernels launched, or <0 on launch error)
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
-                   size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st);
+                   size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st,
+                   const RemapArgs& rm = RemapArgs());
+int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, const short2* map1,
+                 const uint16_t* map2, int out_w, int out_h, uint8_t* d_dst, cudaStream_t st);
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
                     int16_t* gx_out = nullptr, int16_t* gy_out = nullptr);
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);

@@ -24,8 +24,9 @@ class CameraModel:
 
     Reads the reference's calibration XML (calibration/*.xml): in/out size, fx fy cx cy and
     the four distortion coefficients; normalised intrinsics (cx, cy < 1) are rescaled by the
-    input size as in src/CameraModel.cpp:61-68.  Undistortion maps are out of scope: a
-    non-zero first distortion coefficient is reported by IsValid() but not applied.
+    input size as in src/CameraModel.cpp:61-68.  With a non-zero first distortion coefficient
+    the rectify branch (CameraModel.cpp:84-98) runs: new camera matrix for alpha = 1 and the
+    fixed-point undistortion maps, both computed by libuwtrack's host functions.
     """
 
     def __init__(self):
@@ -33,6 +34,8 @@ class CameraModel:
         self.calib = np.zeros(4, np.float32)
         self.dist = np.zeros(4, np.float32)
         self.valid = False
+        self.output_K = None
+        self.map1 = self.map2 = None
 
     def GetCameraModel(self, path):
         root = ET.parse(path).getroot()
@@ -51,7 +54,70 @@ class CameraModel:
             self.calib = self.calib * np.array([self.in_width, self.in_height,
                                                 self.in_width, self.in_height], np.float32)
         self.valid = bool(self.dist[0] != 0)  # CameraModel.cpp:78-83
+        if self.valid:
+            self._rectify()
         return self
+
+    def _original_K(self):
+        K = np.zeros((3, 3), np.float32)
+        K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = (self.calib[0], self.calib[1],
+                                                       self.calib[2], self.calib[3], 1)
+        return K
+
+    def _rectify(self):
+        """CameraModel.cpp:84-98: getOptimalNewCameraMatrix(alpha = 1) + initUndistortRectifyMap
+        (CV_16SC2 fixed-point maps)."""
+        lib = L.load()
+        K = np.ascontiguousarray(self._original_K())
+        d = np.ascontiguousarray(self.dist, np.float32)
+        nK = np.empty((3, 3), np.float32)
+        rc = lib.uwt_camera_optimal_matrix(K.ctypes.data_as(L._fp), d.ctypes.data_as(L._fp),
+                                           self.in_width, self.in_height, 1.0, self.out_width,
+                                           self.out_height, nK.ctypes.data_as(L._fp))
+        if rc != 0:
+            raise UwtError(rc, "uwt_camera_optimal_matrix")
+        self.map1 = np.empty((self.out_height, self.out_width, 2), np.int16)
+        self.map2 = np.empty((self.out_height, self.out_width), np.uint16)
+        rc = lib.uwt_camera_undistort_maps(K.ctypes.data_as(L._fp), d.ctypes.data_as(L._fp),
+                                           nK.ctypes.data_as(L._fp), self.out_width,
+                                           self.out_height, self.map1.ctypes.data_as(L._i16p),
+                                           self.map2.ctypes.data_as(C.POINTER(C.c_uint16)))
+        if rc != 0:
+            raise UwtError(rc, "uwt_camera_undistort_maps")
+        self.output_K = nK
+
+    @classmethod
+    def from_distorted(cls, in_size, out_size, fx, fy, cx, cy, dist):
+        """The rectify branch without an XML file (tests, benches)."""
+        m = cls()
+        m.in_width, m.in_height = in_size
+        m.out_width, m.out_height = out_size
+        m.calib = np.array([fx, fy, cx, cy], np.float32)
+        m.dist = np.asarray(dist, np.float32)
+        m.valid = bool(m.dist[0] != 0)
+        if m.valid:
+            m._rectify()
+        return m
+
+    def Undistort(self, image, device=0):
+        """CameraModel::Undistort (CameraModel.cpp:101-103): remap one host image on the GPU."""
+        img = np.ascontiguousarray(image, np.uint8)
+        out = np.empty((self.out_height, self.out_width), np.uint8)
+        rc = L.load().uwt_undistort_image(device, img.ctypes.data_as(L._u8p), img.shape[1],
+                                          img.shape[0], img.shape[1],
+                                          self.map1.ctypes.data_as(L._i16p),
+                                          self.map2.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                          self.out_width, self.out_height,
+                                          out.ctypes.data_as(L._u8p))
+        if rc != 0:
+            raise UwtError(rc, "uwt_undistort_image")
+        return out
+
+    def GetMap1(self):
+        return self.map1
+
+    def GetMap2(self):
+        return self.map2
 
     @classmethod
     def from_intrinsics(cls, width, height, fx, fy, cx, cy):
@@ -62,10 +128,9 @@ class CameraModel:
         return m
 
     def GetK(self):
-        K = np.zeros((3, 3), np.float32)
-        K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = (self.calib[0], self.calib[1],
-                                                       self.calib[2], self.calib[3], 1)
-        return K
+        # output_intrinsic_camera_: the new matrix when rectifying, else the original
+        # (CameraModel.cpp:78-98)
+        return self.output_K if self.valid else self._original_K()
 
     def GetOutputWidth(self):
         return self.out_width
@@ -81,6 +146,27 @@ class CameraModel:
 
     def IsValid(self):
         return self.valid
+
+
+def CalculateROI(undistorted):
+    """System::CalculateROI (System.cpp:148-191) on the first undistorted image.
+    Returns (x, y, w, h): the crop corner and the new w_, h_."""
+    u = np.ascontiguousarray(undistorted, np.uint8)
+    roi = (C.c_int * 4)()
+    rc = L.load().uwt_calculate_roi(u.ctypes.data_as(L._u8p), u.shape[1], u.shape[0], u.shape[1],
+                                    roi)
+    if rc != 0:
+        raise UwtError(rc, "uwt_calculate_roi: the undistorted image is black on a mid line")
+    return tuple(roi)
+
+
+def AlignROI(roi, levels=5):
+    """The reference lets w_, h_ be whatever CalculateROI finds, which breaks its own pyramid
+    sizing; the tracker needs the width divisible by 16 and both sides by
+    2^(levels-1).  Shrinks the ROI to the largest compliant size, keeping the corner."""
+    x, y, w, h = roi
+    div = max(16, 1 << (levels - 1))
+    return x, y, w // div * div, h // (1 << (levels - 1)) * (1 << (levels - 1))
 
 
 class Frame:
@@ -130,7 +216,24 @@ class Tracker:
         if rc != 0:
             raise UwtError(rc, self._lib.uwt_last_error(None).decode())
         self._h, self.cfg = h, c
+        self._src_w, self._src_h = c.width, c.height
         return self
+
+    # -- System::AddFrame remap + ROI crop, System.cpp:232-235 ------------------------------
+    def SetUndistortion(self, camera, roi_xy=(0, 0)):
+        """After this, AddFrames takes DISTORTED in_width x in_height frames; remap and crop are
+        fused into the pyramid kernel.  camera=None switches it off."""
+        if camera is None:
+            self._check(self._lib.uwt_set_undistortion(self._h, None, None, 0, 0, 0, 0, 0, 0))
+            self._src_w, self._src_h = self.cfg.width, self.cfg.height
+            return
+        m1 = np.ascontiguousarray(camera.GetMap1(), np.int16)
+        m2 = np.ascontiguousarray(camera.GetMap2(), np.uint16)
+        self._check(self._lib.uwt_set_undistortion(
+            self._h, m1.ctypes.data_as(L._i16p), m2.ctypes.data_as(C.POINTER(C.c_uint16)),
+            camera.GetOutputWidth(), camera.GetOutputHeight(), camera.GetInputWidth(),
+            camera.GetInputHeight(), int(roi_xy[0]), int(roi_xy[1])))
+        self._src_w, self._src_h = camera.GetInputWidth(), camera.GetInputHeight()
 
     def close(self):
         if self._h is not None:
@@ -161,9 +264,9 @@ class Tracker:
     def AddFrames(self, slots, frames):
         """frames: u8 array [n, H, W] (or [H, W]) in host memory."""
         a, p, n = self._slots(slots)
-        f = np.ascontiguousarray(frames, np.uint8).reshape(n, self.cfg.height, self.cfg.width)
-        self._check(self._lib.uwt_upload_frames(self._h, n, p, f.ctypes.data, self.cfg.width,
-                                                self.cfg.width * self.cfg.height))
+        f = np.ascontiguousarray(frames, np.uint8).reshape(n, self._src_h, self._src_w)
+        self._check(self._lib.uwt_upload_frames(self._h, n, p, f.ctypes.data, self._src_w,
+                                                self._src_w * self._src_h))
         return [Frame(self, int(s)) for s in a]
 
     def AddFramesHostPtr(self, slots, ptr, row_stride, frame_stride):
@@ -172,8 +275,8 @@ class Tracker:
 
     def AddFramesDevice(self, slots, dev_ptr, row_stride=None, frame_stride=None):
         a, p, n = self._slots(slots)
-        rs = row_stride or self.cfg.width
-        fs = frame_stride or rs * self.cfg.height
+        rs = row_stride or self._src_w
+        fs = frame_stride or rs * self._src_h
         self._check(self._lib.uwt_set_frames_device(self._h, n, p, dev_ptr, rs, fs))
 
     # -- Tracker::ApplyGradient(Frame*), Tracker.cpp:1127 ------------------------------------
