@@ -4,7 +4,8 @@
 // dependency of this library).
 //
 //   reference                                         here
-//   uw::CameraModel   include/CameraModel.h:42-145    uw::CameraModel (pinhole part)
+//   uw::CameraModel   include/CameraModel.h:42-145    uw::CameraModel (pinhole + rectify branch)
+//   System::CalculateROI src/System.cpp:148-191       uw::CalculateROI / uw::AlignROI
 //   uw::Frame         include/System.h:63-103         uw::Frame (a device-side frame slot)
 //   uw::Tracker       include/Tracker.h:90-531        uw::Tracker (direct photometric path)
 //   SE3               include/Options.h (Sophus::SE3f) uw::SE3f (7 floats, Sophus order)
@@ -46,7 +47,7 @@ struct SE3f {
   }
 };
 
-// Pinhole part of uw::CameraModel: reads the reference's calibration XML
+// uw::CameraModel: reads the reference's calibration XML
 // (calibration/*.xml: in/out size, "calibration_values" fx fy cx cy, "rectification").
 class CameraModel {
  public:
@@ -68,7 +69,17 @@ class CameraModel {
       calib_[2] *= in_width_;
       calib_[3] *= in_height_;
     }
-    valid_ = dist_[0] != 0.f;  // CameraModel.cpp:78-83 (rectification itself: out of scope)
+    valid_ = dist_[0] != 0.f;  // CameraModel.cpp:78-83
+    if (valid_) Rectify();
+  }
+  // The rectify branch without an XML file.
+  void SetDistorted(int in_w, int in_h, int out_w, int out_h, float fx, float fy, float cx,
+                    float cy, const float dist4[4]) {
+    in_width_ = in_w; in_height_ = in_h; out_width_ = out_w; out_height_ = out_h;
+    calib_[0] = fx; calib_[1] = fy; calib_[2] = cx; calib_[3] = cy;
+    for (int i = 0; i < 4; ++i) dist_[i] = dist4[i];
+    valid_ = dist_[0] != 0.f;
+    if (valid_) Rectify();
   }
   void SetPinhole(int w, int h, float fx, float fy, float cx, float cy) {
     in_width_ = out_width_ = w;
@@ -76,9 +87,23 @@ class CameraModel {
     calib_[0] = fx; calib_[1] = fy; calib_[2] = cx; calib_[3] = cy;
     valid_ = false;
   }
-  // 3x3 row-major K (CameraModel::GetK, src/CameraModel.cpp:113-115)
-  std::array<float, 9> GetK() const {
+  // 3x3 row-major K (CameraModel::GetK, src/CameraModel.cpp:113-115): output_intrinsic_camera_,
+  // i.e. the new camera matrix when rectifying, else the original one (CameraModel.cpp:78-98)
+  std::array<float, 9> GetK() const { return valid_ ? new_K_ : GetOriginalK(); }
+  std::array<float, 9> GetOriginalK() const {
     return {{calib_[0], 0.f, calib_[2], 0.f, calib_[1], calib_[3], 0.f, 0.f, 1.f}};
+  }
+  // Fixed-point undistortion maps (CV_16SC2 / CV_16UC1 layout), empty when !IsValid()
+  const std::vector<int16_t>& GetMap1() const { return map1_; }
+  const std::vector<uint16_t>& GetMap2() const { return map2_; }
+  // CameraModel::Undistort (src/CameraModel.cpp:101-103): in_w x in_h -> out_w x out_h
+  std::vector<uint8_t> Undistort(const uint8_t* image, size_t row_stride = 0, int device = 0) const {
+    std::vector<uint8_t> out((size_t)out_width_ * out_height_);
+    const int rc = uwt_undistort_image(device, image, in_width_, in_height_,
+                                       row_stride ? row_stride : (size_t)in_width_, map1_.data(),
+                                       map2_.data(), out_width_, out_height_, out.data());
+    if (rc != UWT_OK) throw Error(rc, "uwt_undistort_image failed");
+    return out;
   }
   int GetOutputWidth() const { return out_width_; }
   int GetOutputHeight() const { return out_height_; }
@@ -103,11 +128,47 @@ class CameraModel {
     for (int i = 0; i < 4; ++i)
       if (!(d >> out[i])) throw Error(UWT_E_INVALID, "<" + tag + "> needs 4 values");
   }
+  void Rectify() {  // src/CameraModel.cpp:84-98
+    const std::array<float, 9> K = GetOriginalK();
+    int rc = uwt_camera_optimal_matrix(K.data(), dist_, in_width_, in_height_, 1.0, out_width_,
+                                       out_height_, new_K_.data());
+    if (rc != UWT_OK) throw Error(rc, "getOptimalNewCameraMatrix: bad calibration");
+    map1_.resize((size_t)out_width_ * out_height_ * 2);
+    map2_.resize((size_t)out_width_ * out_height_);
+    rc = uwt_camera_undistort_maps(K.data(), dist_, new_K_.data(), out_width_, out_height_,
+                                   map1_.data(), map2_.data());
+    if (rc != UWT_OK) throw Error(rc, "initUndistortRectifyMap: singular camera matrix");
+  }
   int in_width_ = 0, in_height_ = 0, out_width_ = 0, out_height_ = 0;
+  std::array<float, 9> new_K_{{0, 0, 0, 0, 0, 0, 0, 0, 1}};
+  std::vector<int16_t> map1_;
+  std::vector<uint16_t> map2_;
   float calib_[4] = {0, 0, 0, 0};
   float dist_[4] = {0, 0, 0, 0};
   bool valid_ = false;
 };
+
+// System::CalculateROI (src/System.cpp:148-191) on the first undistorted image.
+struct Rect {
+  int x = 0, y = 0, width = 0, height = 0;
+};
+inline Rect CalculateROI(const std::vector<uint8_t>& undistorted, int w, int h) {
+  int r[4];
+  const int rc = uwt_calculate_roi(undistorted.data(), w, h, (size_t)w, r);
+  if (rc != UWT_OK) throw Error(rc, "CalculateROI: the undistorted image is black on a mid line");
+  Rect o;
+  o.x = r[0]; o.y = r[1]; o.width = r[2]; o.height = r[3];
+  return o;
+}
+// The reference takes w_, h_ from the ROI as found, which breaks its own pyramid sizing
+// (w>>l vs cv::resize rounding); this library needs width % 16 == 0 and both sides divisible
+// by 2^(levels-1): shrink the ROI to the largest compliant size, keeping the corner.
+inline Rect AlignROI(Rect r, int levels = 5) {
+  const int dv = 1 << (levels - 1), dw = dv > 16 ? dv : 16;
+  r.width = r.width / dw * dw;
+  r.height = r.height / dv * dv;
+  return r;
+}
 
 class Tracker;
 
@@ -153,6 +214,7 @@ class Tracker {
     cfg_.fx = K[0]; cfg_.fy = K[4]; cfg_.cx = K[2]; cfg_.cy = K[5];
     if (h_) uwt_destroy(h_);
     h_ = nullptr;
+    src_w_ = src_h_ = 0;
     const int rc = uwt_create(&cfg_, &h_);
     if (rc != UWT_OK) throw Error(rc, uwt_last_error(nullptr));
     w_.clear(); h__.clear(); fx_.clear(); fy_.clear(); cx_.clear(); cy_.clear();
@@ -163,12 +225,21 @@ class Tracker {
       fx_.push_back(li.fx); fy_.push_back(li.fy); cx_.push_back(li.cx); cy_.push_back(li.cy);
     }
   }
+  // System::AddFrame `remap(..); images_[0] = distortion(ROI)` (src/System.cpp:232-235): after
+  // this, AddFrame takes DISTORTED in_w x in_h frames; remap + crop run inside the pyramid kernel.
+  void SetUndistortion(const CameraModel& cam, int roi_x, int roi_y) {
+    Check(uwt_set_undistortion(h_, cam.GetMap1().data(), cam.GetMap2().data(),
+                               cam.GetOutputWidth(), cam.GetOutputHeight(), cam.GetInputWidth(),
+                               cam.GetInputHeight(), roi_x, roi_y));
+    src_w_ = cam.GetInputWidth();
+    src_h_ = cam.GetInputHeight();
+  }
   void InitializeMasks() {}  // dead weight in the reference (Tracker.cpp:342-359): no-op
 
   // System::AddFrame (src/System.cpp:225-262): gray 8-bit frame -> slot, builds the pyramid.
   Frame AddFrame(int slot, const uint8_t* gray, size_t row_stride = 0) {
-    const size_t rs = row_stride ? row_stride : (size_t)cfg_.width;
-    Check(uwt_upload_frames(h_, 1, &slot, gray, rs, rs * cfg_.height));
+    const size_t rs = row_stride ? row_stride : (size_t)(src_w_ ? src_w_ : cfg_.width);
+    Check(uwt_upload_frames(h_, 1, &slot, gray, rs, rs * (src_h_ ? src_h_ : cfg_.height)));
     Frame f;
     f.slot = slot;
     f.tracker_ = this;
@@ -207,6 +278,7 @@ class Tracker {
   }
   uwt_config cfg_;
   uwt_tracker* h_ = nullptr;
+  int src_w_ = 0, src_h_ = 0;  // distorted input size when undistortion is on
 };
 
 inline std::vector<uint8_t> Frame::images(int lvl) const {

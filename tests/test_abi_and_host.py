@@ -138,12 +138,16 @@ def test_camera_model_reads_the_reference_xml_schema(tmp_path):
     # TUM-mono convention: normalised intrinsics are rescaled (CameraModel.cpp:61-68)
     p2 = tmp_path / "mono.xml"
     p2.write_text(CALIB_XML.format(iw=1280, ih=1024, ow=1280, oh=1024,
-                                   c="0.5357 0.6696 0.4932 0.5004", d="0.9 0 0 0"))
+                                   c="0.5357 0.6696 0.4932 0.5004", d="-0.2 0.04 0 0"))
     m2 = U.CameraModel().GetCameraModel(str(p2))
-    K2 = m2.GetK()
+    K2 = m2._original_K()
     assert K2[0, 0] == np.float32(0.5357) * np.float32(1280)
     assert K2[1, 2] == np.float32(0.5004) * np.float32(1024)
+    # non-zero distortion: the rectify branch runs (CameraModel.cpp:84-98) and GetK() is the
+    # new camera matrix; maps have the output size
     assert m2.IsValid()
+    assert m2.GetK()[0, 0] != K2[0, 0] and m2.GetK()[2, 2] == 1
+    assert m2.GetMap1().shape == (1024, 1280, 2) and m2.GetMap2().shape == (1024, 1280)
 
 
 def test_synth_is_seeded_and_consistent():

@@ -117,7 +117,7 @@ CALIB_XML = """<?xml version="1.0"?>
 <calibration_values type_id="opencv-matrix"><rows>1</rows><cols>4</cols><dt>f</dt>
   <data> {fx} {fy} {cx} {cy} </data></calibration_values>
 <rectification type_id="opencv-matrix"><rows>1</rows><cols>4</cols><dt>f</dt>
-  <data> 0 0 0 1 </data></rectification>
+  <data> {dist} </data></rectification>
 </opencv_storage>
 """
 
@@ -132,7 +132,8 @@ def test_cpp_facade_example_tracks_a_sequence(tmp_path, oracle):
                            "-Wl,-rpath," + os.path.dirname(so), "-o", str(exe)])
     calib = "small"
     w, h, fx, fy, cx, cy = synth.CALIB[calib]
-    (tmp_path / "c.xml").write_text(CALIB_XML.format(w=w, h=h, fx=fx, fy=fy, cx=cx, cy=cy))
+    (tmp_path / "c.xml").write_text(CALIB_XML.format(w=w, h=h, fx=fx, fy=fy, cx=cx, cy=cy,
+                                                     dist="0 0 0 1"))
     frames, _, _ = synth.render_sequence(calib, 4, 5, rot=3e-3, trans=3e-3)
     np.stack(frames).tofile(str(tmp_path / "f.raw"))
     out = subprocess.check_output([str(exe), str(tmp_path / "c.xml"), str(tmp_path / "f.raw"),
@@ -141,4 +142,41 @@ def test_cpp_facade_example_tracks_a_sequence(tmp_path, oracle):
                      np.float32)
     assert poses.shape == (4, 7)
     ref, _, _ = oracle.track_sequence(oracle.default_params(w, h, fx, fy, cx, cy), np.stack(frames))
+    assert np.array_equal(poses, ref)
+
+
+def test_cpp_facade_example_rectifies_and_tracks(tmp_path, oracle):
+    # the rectify branch end to end in C++: CameraModel (maps), Undistort, CalculateROI, the
+    # fused remap + crop + pyramid, tracking -- against the oracle pipeline on the same frames
+    from uw_slam_b200 import build
+    so = build.build()
+    exe = tmp_path / "track_sequence"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "track_sequence.cpp"),
+                           "-L", os.path.dirname(so), "-luwtrack",
+                           "-Wl,-rpath," + os.path.dirname(so), "-o", str(exe)])
+    w, h, fx, fy, cx, cy = 320, 240, 230.0, 228.0, 158.0, 121.5
+    dist = [-0.25, 0.06, 0.0005, -0.0003]
+    (tmp_path / "c.xml").write_text(CALIB_XML.format(
+        w=w, h=h, fx=fx, fy=fy, cx=cx, cy=cy, dist=" ".join("%.9g" % v for v in dist)))
+    synth.CALIB["_facade_und"] = (w, h, fx, fy, cx, cy)
+    frames, _, _ = synth.render_sequence("_facade_und", 3, 4, rot=3e-3, trans=3e-3)
+    frames = np.maximum(np.stack(frames), 1)
+    frames.tofile(str(tmp_path / "f.raw"))
+    out = subprocess.check_output([str(exe), str(tmp_path / "c.xml"), str(tmp_path / "f.raw"),
+                                   "4"], text=True)
+    poses = np.array([[np.float32(v) for v in ln.split()] for ln in out.strip().splitlines()],
+                     np.float32)
+    assert poses.shape == (3, 7)
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    d = np.array(dist, np.float32)
+    nK = oracle.optimal_new_camera_matrix(K, d, (w, h), 1.0, (w, h))
+    m1, m2 = oracle.init_undistort_rectify_map(K, d, nK, (w, h))
+    und = [oracle.remap_bilinear(f, m1, m2) for f in frames]
+    x, y, rw, rh = oracle.calculate_roi(und[0])
+    rw, rh = rw // 16 * 16, rh // 16 * 16
+    crop = np.stack([u[y:y + rh, x:x + rw] for u in und])
+    p = oracle.default_params(rw, rh, float(nK[0, 0]), float(nK[1, 1]), float(nK[0, 2]),
+                              float(nK[1, 2]))
+    ref, _, _ = oracle.track_sequence(p, crop)
     assert np.array_equal(poses, ref)
