@@ -18,6 +18,8 @@
 //             the packed 8-byte record (x, y, I1, gx, gy) the Gauss-Newton kernel streams;
 //             I1 and the Scharr gx, gy of a selected pixel come from an image tile with a
 //             one-pixel halo in shared memory (no int16 gradient planes are read).
+#include <algorithm>
+
 #include "uwt_internal.cuh"
 
 namespace uwt {
@@ -44,6 +46,21 @@ __device__ __forceinline__ TileItem locate_item(const Geom& geom, int item) {
 
 constexpr int kTilePitch8 = kStripW + 4;    // bytes per u8 tile row: 33 words -> no conflicts
 
+// 4-byte asynchronous global -> shared copy (LDGSTS); `valid == false` writes zeros.  The count
+// and scatter kernels are persistent: while the tile of one work item is processed, the copies
+// of the next item are already in flight into the other shared-memory buffer.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Loads the (kSegRows x kStripW) u8 tile at (x0, y0) row-wise into shared memory.
 __device__ __forceinline__ void load_tile_u8(const uint8_t* __restrict__ plane, const LevelGeom& L,
                                              int x0, int y0, uint8_t* tile, int t) {
@@ -52,9 +69,9 @@ __device__ __forceinline__ void load_tile_u8(const uint8_t* __restrict__ plane, 
 #pragma unroll
   for (int j = 0; j < kSegRows / 8; ++j) {
     const int row = wid + 8 * j, gy = y0 + row;
-    uint32_t v = 0;
-    if (gy < L.h && gx < L.pitch) v = *reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx);
-    *reinterpret_cast<uint32_t*>(tile + row * kTilePitch8 + lane * 4) = v;
+    const bool ok = gy < L.h && gx < L.pitch;
+    cp_async4(tile + row * kTilePitch8 + lane * 4, ok ? plane + (size_t)gy * L.pitch + gx : plane,
+              ok);
   }
 }
 
@@ -71,60 +88,114 @@ __device__ __forceinline__ void load_img_tile_halo(const uint8_t* __restrict__ p
   for (int i = t; i < kImgTileRows * kImgTileWords; i += 256) {
     const int row = i / kImgTileWords, j = i % kImgTileWords;
     const int gy = y0 - 1 + row, gx = x0 - 4 + 4 * j;
-    uint32_t v = 0;
-    if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch)
-      v = *reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx);
-    *reinterpret_cast<uint32_t*>(tile + row * kImgTilePitch + 4 * j) = v;
+    const bool ok = gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch;
+    cp_async4(tile + row * kImgTilePitch + 4 * j, ok ? plane + (size_t)gy * L.pitch + gx : plane,
+              ok);
   }
 }
 
-// Scharr x / y at image pixel (x, y) from the halo tile (Tracker.cpp:1133-1134),
-// BORDER_REFLECT_101 by index mapping: the same integers as K2's gradient_kernel.
-__device__ __forceinline__ void scharr_from_tile(const uint8_t* tile, const LevelGeom& L, int x0,
-                                                 int y0, int x, int y, int& gx, int& gy,
-                                                 int& center) {
-  const int xm = (x == 0) ? 1 : x - 1, xp = (x + 1 >= L.w) ? L.w - 2 : x + 1;
-  const int ym = (y == 0) ? 1 : y - 1, yp = (y + 1 >= L.h) ? L.h - 2 : y + 1;
-  const uint8_t* rm = tile + (ym - (y0 - 1)) * kImgTilePitch - (x0 - 4);
-  const uint8_t* r0 = tile + (y - (y0 - 1)) * kImgTilePitch - (x0 - 4);
-  const uint8_t* rp = tile + (yp - (y0 - 1)) * kImgTilePitch - (x0 - 4);
-  const int a = rm[xm], b = rm[x], cc = rm[xp];
-  const int d = r0[xm], f = r0[xp];
-  const int g = rp[xm], h = rp[x], i = rp[xp];
-  center = r0[x];
-  gx = 3 * (cc - a) + 10 * (f - d) + 3 * (i - g);
-  gy = 3 * (g - a) + 10 * (h - b) + 3 * (i - cc);
+// Scharr x / y at image pixel (x, y) from the halo tile (Tracker.cpp:1133-1134): the same
+// integers as K2's gradient_kernel.  BORDER_REFLECT_101 is already written into the halo
+// (patch_img_tile_borders), so a pixel is three unaligned 4-byte windows and five dp4a.
+__device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
+  return d;
+}
+__device__ __forceinline__ uint32_t window_at(const uint8_t* tile, int off) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(tile + (off & ~3));
+  return __funnelshift_r(p[0], p[1], 8 * (off & 3));
+}
+__device__ __forceinline__ void scharr_from_tile(const uint8_t* tile, int x0, int y0, int x, int y,
+                                                 int& gx, int& gy, int& center) {
+  // byte offset of pixel (x - 1, y - 1) inside the tile
+  const int off = (y - y0) * kImgTilePitch + (x - x0 + 3);
+  const uint32_t top = window_at(tile, off);
+  const uint32_t mid = window_at(tile, off + kImgTilePitch);
+  const uint32_t bot = window_at(tile, off + 2 * kImgTilePitch);
+  center = (mid >> 8) & 0xFF;
+  gx = dp4a_us(top, 0x000300FDu, dp4a_us(mid, 0x000A00F6u, dp4a_us(bot, 0x000300FDu, 0)));
+  gy = dp4a_us(bot, 0x00030A03u, dp4a_us(top, 0x00FDF6FDu, 0));
 }
 
+// Writes the reflected border pixels (x = -1 -> 1, x = w -> w-2, then y = -1 -> 1, y = h -> h-2)
+// into the halo of an image tile.  Block-wide; only tiles on the image border do any work.
+__device__ __forceinline__ void patch_img_tile_borders(uint8_t* tile, const LevelGeom& L, int x0,
+                                                       int y0, int t) {
+  const bool edge_l = (x0 == 0), edge_r = (x0 + kStripW >= L.w);
+  const bool edge_t = (y0 == 0), edge_b = (y0 + kSegRows >= L.h);
+  if (edge_l || edge_r) {
+    if (t < kImgTileRows) {
+      uint8_t* row = tile + t * kImgTilePitch;
+      if (edge_l) row[3] = row[5];
+      if (edge_r) {
+        const int cx = L.w - x0 + 4;
+        row[cx] = row[cx - 2];
+      }
+    }
+    __syncthreads();
+  }
+  if (edge_t || edge_b) {
+    constexpr int kRowWords = kImgTilePitch / 4;
+    if (t < kRowWords) {
+      uint32_t* rows = reinterpret_cast<uint32_t*>(tile);
+      if (edge_t) rows[t] = rows[2 * kRowWords + t];
+      if (edge_b) {
+        const int ry = L.h - (y0 - 1);  // tile row of image row h
+        rows[ry * kRowWords + t] = rows[(ry - 2) * kRowWords + t];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// count: no shared-memory staging.  A thread reads 32-bit words (4 pixels of one row, coalesced
+// across the warp), compares the four bytes against the threshold at once (SWAR) and adds the
+// 0/1 results into four packed byte counters: a (column, 64-row segment) count is at most 64.
 __global__ void __launch_bounds__(256)
 cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                  const int* __restrict__ slots) {
-  __shared__ __align__(16) uint8_t sg[kSegRows * kTilePitch8];
+                  const int* __restrict__ slots, int n_slots) {
+  __shared__ uint32_t part[8][32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const TileItem it = locate_item(geom, blockIdx.x);
-  const int slot = slots[blockIdx.y];
-  const LevelGeom& L = geom.lv[it.lvl];
-  const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
-  const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
-  load_tile_u8(pools.g + (size_t)slot * geom.plane_elems + L.plane_off, L, x0, y0, sg, t);
-  __syncthreads();
-  // warp `wid` owns tile columns [16 wid, 16 wid + 16); lane = row within a 32-row chunk
-  uint32_t mine = 0;
-#pragma unroll 4
-  for (int j = 0; j < 16; ++j) {
-    const int c = wid * 16 + j;
-    uint32_t cnt = 0;
+  const int total = geom.warp_items_total * n_slots;
+  constexpr int kRowsPerWarp = kSegRows / 8;
+  for (int work = blockIdx.x; work < total; work += gridDim.x) {
+    const TileItem it = locate_item(geom, work % geom.warp_items_total);
+    const int slot = slots[work / geom.warp_items_total];
+    const LevelGeom& L = geom.lv[it.lvl];
+    const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
+    const int ithr = pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
+    const uint8_t* plane = pools.g + (size_t)slot * geom.plane_elems + L.plane_off;
+    const int gx = x0 + lane * 4;
+    uint32_t acc = 0;
+    if (ithr < 255 && gx < L.pitch) {  // g <= 255: a threshold of 255 or more selects nothing
+      const uint32_t thr4 = (uint32_t)ithr * 0x01010101u;
+      uint32_t w[kRowsPerWarp];
 #pragma unroll
-    for (int ch = 0; ch < kSegRows / 32; ++ch) {
-      const int row = ch * 32 + lane;
-      const bool sel = (y0 + row < L.h) && ((uint32_t)sg[row * kTilePitch8 + c] > ithr);
-      cnt += __popc(__ballot_sync(0xffffffffu, sel));
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int gy = y0 + wid * kRowsPerWarp + r;
+        // row-pitch padding beyond the image width is zero (never written), so it never counts
+        w[r] = (gy < L.h) ? __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx))
+                          : 0u;
+      }
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) acc += __vsetgtu4(w[r], thr4);
     }
-    if (lane == j) mine = cnt;
+    part[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += part[k][lane];  // bytes stay <= 64: no carry
+      uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = gx + i;
+        if (x < L.w) cnt[(size_t)x * L.nseg + it.seg] = (sum >> (8 * i)) & 0xFFu;
+      }
+    }
+    __syncthreads();
   }
-  const int x = x0 + wid * 16 + lane;
-  if (lane < 16 && x < L.w)
-    pools.cnt[(size_t)slot * geom.cnt_elems + L.cnt_off + (size_t)x * L.nseg + it.seg] = mine;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -171,61 +242,99 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
 
 __global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                    const int* __restrict__ slots) {
-  __shared__ __align__(16) uint8_t sg[kSegRows * kTilePitch8];
-  __shared__ __align__(16) uint8_t si[kImgTileRows * kImgTilePitch];
+                    const int* __restrict__ slots, int n_slots) {
+  __shared__ __align__(16) uint8_t sg[2][kSegRows * kTilePitch8];
+  __shared__ __align__(16) uint8_t si[2][kImgTileRows * kImgTilePitch];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const TileItem it = locate_item(geom, blockIdx.x);
-  const int slot = slots[blockIdx.y];
-  const LevelGeom& L = geom.lv[it.lvl];
-  const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
-  const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
-  const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off;
-  const bool has_rec = L.rec_off >= 0;
-  load_tile_u8(pools.g + pbase, L, x0, y0, sg, t);
-  if (has_rec) load_img_tile_halo(pools.img + pbase, L, x0, y0, si, t);
-  __syncthreads();
-  const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
-  uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
-  uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
+  const int total = geom.warp_items_total * n_slots;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  // start offsets of this warp's 16 (column, segment) runs: one per lane
-  uint32_t my_base = 0;
-  {
-    const int x = x0 + wid * 16 + lane;
-    if (lane < 16 && x < L.w) my_base = cnt[(size_t)x * L.nseg + it.seg];
-  }
-#pragma unroll 2
-  for (int j = 0; j < 16; ++j) {
-    const int c = wid * 16 + j, x = x0 + c;
-    uint32_t base = __shfl_sync(0xffffffffu, my_base, j);
-    if (x >= L.w) break;  // warp-uniform
-#pragma unroll
-    for (int ch = 0; ch < kSegRows / 32; ++ch) {
-      const int row = ch * 32 + lane, y = y0 + row;
-      const bool sel = (y < L.h) && ((uint32_t)sg[row * kTilePitch8 + c] > ithr);
-      const uint32_t b = __ballot_sync(0xffffffffu, sel);
-      if (sel) {
-        const uint32_t o = base + __popc(b & lt_mask);
-        xy[o] = (uint32_t)x | ((uint32_t)y << 16);
-        if (has_rec) {
-          int gx, gy, i1;
-          scharr_from_tile(si, L, x0, y0, x, y, gx, gy, i1);
-          rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
-        }
-      }
-      base += __popc(b);
+  auto issue = [&](int work, int buf) {
+    const TileItem it = locate_item(geom, work % geom.warp_items_total);
+    const int slot = slots[work / geom.warp_items_total];
+    const LevelGeom& L = geom.lv[it.lvl];
+    const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off;
+    load_tile_u8(pools.g + pbase, L, it.strip * kStripW, it.seg * kSegRows, sg[buf], t);
+    if (L.rec_off >= 0)
+      load_img_tile_halo(pools.img + pbase, L, it.strip * kStripW, it.seg * kSegRows, si[buf], t);
+    cp_async_commit();
+  };
+  int work = blockIdx.x, buf = 0;
+  if (work < total) issue(work, 0);
+  for (; work < total; work += gridDim.x, buf ^= 1) {
+    const int next = work + gridDim.x;
+    if (next < total) {
+      issue(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
+    __syncthreads();
+    const TileItem it = locate_item(geom, work % geom.warp_items_total);
+    const int slot = slots[work / geom.warp_items_total];
+    const LevelGeom& L = geom.lv[it.lvl];
+    const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
+    const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
+    const bool has_rec = L.rec_off >= 0;
+    const uint8_t* tg = sg[buf];
+    const uint8_t* ti = si[buf];
+    if (has_rec) patch_img_tile_borders(si[buf], L, x0, y0, t);
+    const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
+    uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
+    uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
+    // start offsets of this warp's 16 (column, segment) runs: one per lane
+    uint32_t my_base = 0;
+    {
+      const int x = x0 + wid * 16 + lane;
+      if (lane < 16 && x < L.w) my_base = cnt[(size_t)x * L.nseg + it.seg];
+    }
+#pragma unroll 2
+    for (int j = 0; j < 16; ++j) {
+      const int c = wid * 16 + j, x = x0 + c;
+      uint32_t base = __shfl_sync(0xffffffffu, my_base, j);
+      if (x >= L.w) break;  // warp-uniform
+#pragma unroll
+      for (int ch = 0; ch < kSegRows / 32; ++ch) {
+        const int row = ch * 32 + lane, y = y0 + row;
+        const bool sel = (y < L.h) && ((uint32_t)tg[row * kTilePitch8 + c] > ithr);
+        const uint32_t b = __ballot_sync(0xffffffffu, sel);
+        if (sel) {
+          const uint32_t o = base + __popc(b & lt_mask);
+          xy[o] = (uint32_t)x | ((uint32_t)y << 16);
+          if (has_rec) {
+            int gx, gy, i1;
+            scharr_from_tile(ti, x0, y0, x, y, gx, gy, i1);
+            rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
+          }
+        }
+        base += __popc(b);
+      }
+    }
+    __syncthreads();  // both buffers of this stage are refilled in the next iteration
   }
 }
 
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st) {
-  dim3 grid(g.warp_items_total, n);
-  cand_count_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
+  // persistent grids: a multiple of the 148 SMs, as many CTAs per SM as the double-buffered
+  // tiles allow; small jobs get one CTA per work item
+  const long long total = (long long)g.warp_items_total * n;
+  static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, cand_count_kernel, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, cand_scatter_kernel, 256, 0);
+    if (sms <= 0) sms = 148;
+    if (per_sm_count <= 0) per_sm_count = 4;
+    if (per_sm_scatter <= 0) per_sm_scatter = 4;
+  }
+  const int grid_count = (int)std::min<long long>(total, (long long)sms * per_sm_count);
+  const int grid_scatter = (int)std::min<long long>(total, (long long)sms * per_sm_scatter);
+  cand_count_kernel<<<grid_count, 256, 0, st>>>(g, p, d_slots, n);
   if (cudaGetLastError() != cudaSuccess) return -1;
   cand_scan_kernel<<<dim3(g.levels, n), 1024, 0, st>>>(g, p, d_slots);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scatter_kernel<<<grid, 256, 0, st>>>(g, p, d_slots);
+  cand_scatter_kernel<<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 3;
 }

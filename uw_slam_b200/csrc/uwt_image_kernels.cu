@@ -226,36 +226,32 @@ constexpr int kHaloX = 16;                               // 16-byte aligned halo
 constexpr int kTileRowBytes = kGradTileW + 2 * kHaloX;   // 160
 constexpr int kTileRows = kGradTileH + 2;                // 34
 
-struct RowVals {
-  int hx[4];  // v[i+1] - v[i-1]
-  int sm[4];  // 3 v[i-1] + 10 v[i] + 3 v[i+1]
-};
+// dp4a with unsigned pixel bytes and signed stencil weights (SASS: IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
+  return d;
+}
+// Scharr rows as packed signed bytes over a 4-byte window (left, centre, right, unused)
+constexpr uint32_t kW_m3_0_3 = 0x000300FDu;     // (-3, 0, 3, 0)
+constexpr uint32_t kW_m10_0_10 = 0x000A00F6u;   // (-10, 0, 10, 0)
+constexpr uint32_t kW_3_10_3 = 0x00030A03u;     // (3, 10, 3, 0)
+constexpr uint32_t kW_m3_m10_m3 = 0x00FDF6FDu;  // (-3, -10, -3, 0)
 
-__device__ __forceinline__ RowVals row_vals(const uint8_t* srow, int sx, bool left_edge,
-                                            bool right_edge, int nvalid) {
-  // srow: tile row in shared memory; sx: byte index of the 4-pixel group (multiple of 4)
+// The four 3-pixel windows of a 4-pixel group: window i = bytes [sx-1+i, sx+2+i] of the row.
+struct RowWin {
+  uint32_t w[4];
+};
+__device__ __forceinline__ RowWin row_windows(const uint8_t* srow, int sx) {
+  const uint32_t l = *reinterpret_cast<const uint32_t*>(srow + sx - 4);
   const uint32_t c = *reinterpret_cast<const uint32_t*>(srow + sx);
-  int v[6];
-  v[1] = c & 0xFF;
-  v[2] = (c >> 8) & 0xFF;
-  v[3] = (c >> 16) & 0xFF;
-  v[4] = c >> 24;
-  v[0] = left_edge ? v[2] : srow[sx - 1];  // REFLECT_101: x = -1 -> 1
-  v[5] = srow[sx + 4];
-  if (right_edge) {
-    // the image ends inside this group after nvalid pixels: x = w -> w - 2
-    if (nvalid == 4) v[5] = v[3];
-    else if (nvalid == 3) v[4] = v[2];
-    else if (nvalid == 2) v[3] = v[1];
-    else v[2] = v[0];
-  }
-  RowVals r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    r.hx[i] = v[i + 2] - v[i];
-    r.sm[i] = 3 * v[i] + 10 * v[i + 1] + 3 * v[i + 2];
-  }
-  return r;
+  const uint32_t r = *reinterpret_cast<const uint32_t*>(srow + sx + 4);
+  RowWin o;
+  o.w[0] = __funnelshift_r(l, c, 24);
+  o.w[1] = c;
+  o.w[2] = __funnelshift_r(c, r, 8);
+  o.w[3] = __funnelshift_r(c, r, 16);
+  return o;
 }
 
 template <bool kPlanes>
@@ -300,59 +296,86 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
   }
   mbar_wait(&bar, 0);
 
-  // ---- compute: warp = 4 rows, lane = 4 pixels ----
+  // ---- BORDER_REFLECT_101 written into the halo once, so the stencil loop has no edge cases:
+  //      x = -1 -> 1, x = w -> w - 2 (columns first), then y = -1 -> 1, y = h -> h - 2 (rows,
+  //      including the patched columns).  Only tiles on the image border take these branches.
+  const bool edge_l = (x0 == 0), edge_r = (x0 + kGradTileW >= L.w);
+  const bool edge_t = (y0 == 0), edge_b = (y0 + kGradTileH >= L.h);
+  if (edge_l || edge_r) {
+    if (t < kTileRows) {
+      if (edge_l) tile[t][kHaloX - 1] = tile[t][kHaloX + 1];
+      if (edge_r) {
+        const int cx = kHaloX + (L.w - x0);
+        tile[t][cx] = tile[t][cx - 2];
+      }
+    }
+    __syncthreads();
+  }
+  if (edge_t || edge_b) {
+    if (t < kTileRowBytes / 4) {
+      uint32_t* rows = reinterpret_cast<uint32_t*>(&tile[0][0]);
+      constexpr int kRowWords = kTileRowBytes / 4;
+      if (edge_t) rows[t] = rows[2 * kRowWords + t];
+      if (edge_b) {
+        const int ry = L.h - (y0 - 1);  // tile row of image row h
+        rows[ry * kRowWords + t] = rows[(ry - 2) * kRowWords + t];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- compute: warp = 4 rows, lane = 4 pixels; 5 dp4a per pixel (3 for gx, 2 for gy) ----
   const int lane = t & 31, wy = t >> 5;
   const int xg = x0 + lane * 4;
   const int sx = kHaloX + lane * 4;
   uint32_t gsum = 0;
-  if (xg < L.w) {
+  const int ybase = y0 + wy * 4;
+  if (xg < L.w && ybase < L.h) {
     const int nvalid = min(4, L.w - xg);
-    const bool left_edge = (xg == 0);
-    const bool right_edge = (xg + 4 >= L.w);
-    const int ybase = y0 + wy * 4;
-    auto srow = [&](int y) -> const uint8_t* {
-      // REFLECT_101 on rows: -1 -> 1, h -> h - 2
-      const int yy = y < 0 ? -y : (y >= L.h ? 2 * L.h - 2 - y : y);
-      return tile[yy - (y0 - 1)];
-    };
-    if (ybase < L.h) {
-      RowVals rm = row_vals(srow(ybase - 1), sx, left_edge, right_edge, nvalid);
-      RowVals r0 = row_vals(srow(ybase), sx, left_edge, right_edge, nvalid);
+    const uint32_t vmask = nvalid == 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+    const uint8_t* trow = &tile[wy * 4][0];  // tile row of image row ybase - 1
+    RowWin top = row_windows(trow, sx);
+    RowWin mid = row_windows(trow + kTileRowBytes, sx);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int y = ybase + j;
-        if (y >= L.h) break;
-        RowVals rp = row_vals(srow(y + 1), sx, left_edge, right_edge, nvalid);
-        int vx[4], vy[4];
-        uint32_t gq = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int y = ybase + j;
+      if (y >= L.h) break;
+      const RowWin bot = row_windows(trow + (j + 2) * kTileRowBytes, sx);
+      int vx[4], vy[4];
+      uint32_t ax = 0, ay = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          vx[i] = 3 * rm.hx[i] + 10 * r0.hx[i] + 3 * rp.hx[i];
-          vy[i] = rp.sm[i] - rm.sm[i];
-          const int ax = min(abs(vx[i]), 255), ay = min(abs(vy[i]), 255);
-          const int s = ax + ay;
-          const uint32_t gv = (uint32_t)((s + ((s >> 1) & 1)) >> 1);  // ties to even
-          if (i < nvalid) gsum += gv;
-          gq |= gv << (8 * i);
-        }
-        const size_t o = plane_base + (size_t)y * L.pitch + xg;
-        if (nvalid == 4) {
-          *reinterpret_cast<uint32_t*>(pools.g + o) = gq;
-        } else {
-          for (int i = 0; i < nvalid; ++i) pools.g[o + i] = (uint8_t)(gq >> (8 * i));
-        }
-        if (kPlanes) {
-          // gradientX_/gradientY_ planes are materialised only on request (read-back): the
-          // tracker itself consumes the gradients through the packed candidate records
-          const size_t po = (size_t)L.plane_off + (size_t)y * L.pitch + xg;
-          for (int i = 0; i < nvalid; ++i) {
-            gx_out[po + i] = (int16_t)vx[i];
-            gy_out[po + i] = (int16_t)vy[i];
-          }
-        }
-        rm = r0;
-        r0 = rp;
+      for (int i = 0; i < 4; ++i) {
+        // Tracker.cpp:1133-1134: Scharr x / y, CV_16S
+        vx[i] = dp4a_us(top.w[i], kW_m3_0_3,
+                        dp4a_us(mid.w[i], kW_m10_0_10, dp4a_us(bot.w[i], kW_m3_0_3, 0)));
+        vy[i] = dp4a_us(bot.w[i], kW_3_10_3, dp4a_us(top.w[i], kW_m3_m10_m3, 0));
+        // Tracker.cpp:1139-1140: convertScaleAbs -> min(|v|, 255), packed 4 x u8
+        ax |= (uint32_t)min(abs(vx[i]), 255) << (8 * i);
+        ay |= (uint32_t)min(abs(vy[i]), 255) << (8 * i);
       }
+      // Tracker.cpp:1142: addWeighted(.5, .5) = (ax + ay) / 2, ties to even, on 4 bytes at once:
+      // floor average, plus one where the sum is odd and the floor is odd
+      const uint32_t x_or = ax ^ ay;
+      const uint32_t fl = (ax & ay) + ((x_or >> 1) & 0x7F7F7F7Fu);
+      const uint32_t gq = fl + (x_or & fl & 0x01010101u);
+      gsum = __dp4a(gq & vmask, 0x01010101u, gsum);
+      const size_t o = plane_base + (size_t)y * L.pitch + xg;
+      if (nvalid == 4) {
+        *reinterpret_cast<uint32_t*>(pools.g + o) = gq;
+      } else {
+        for (int i = 0; i < nvalid; ++i) pools.g[o + i] = (uint8_t)(gq >> (8 * i));
+      }
+      if (kPlanes) {
+        // gradientX_/gradientY_ planes are materialised only on request (read-back): the
+        // tracker itself consumes the gradients through the packed candidate records
+        const size_t po = (size_t)L.plane_off + (size_t)y * L.pitch + xg;
+        for (int i = 0; i < nvalid; ++i) {
+          gx_out[po + i] = (int16_t)vx[i];
+          gy_out[po + i] = (int16_t)vy[i];
+        }
+      }
+      top = mid;
+      mid = bot;
     }
   }
 
