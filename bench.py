@@ -146,7 +146,7 @@ def ncu_traffic(batch):
     return None
 
 
-def cpu_tracks(frames_np, threads, accum_mode=0):
+def cpu_tracks(frames_np, threads, accum_mode=0, weight_mode=0):
     """Runs the oracle's reference-shaped loop on [n_seq, n_frames, H, W] host frames with
     `threads` concurrent single-threaded trackers.  Returns (tracks, seconds, poses)."""
     from oracle import uw_oracle as O
@@ -157,7 +157,8 @@ def cpu_tracks(frames_np, threads, accum_mode=0):
     O.lib()
 
     def work(ids):
-        p = O.default_params(w, h, fx, fy, cx, cy, accum_mode=accum_mode, threads=1)
+        p = O.default_params(w, h, fx, fy, cx, cy, accum_mode=accum_mode, threads=1,
+                             weight_mode=weight_mode)
         for s in ids:
             poses[s], _, _ = O.track_sequence(p, frames_np[s])
 
@@ -234,7 +235,9 @@ def run_ours(args):
     t = U.Tracker(False)
     t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
                         max_frames=2 * B, device=local_rank, cluster_size=args.cluster,
-                        flags=(L.FLAG_DMMA_ACCUM if args.dmma_accum else 0))
+                        flags=(L.FLAG_DMMA_ACCUM if args.dmma_accum else 0) |
+                        (L.FLAG_CLUSTER_KERNEL if args.cluster_kernel else 0),
+                        weight_mode=args.weights)
     stream = torch.cuda.ExternalStream(t.stream_ptr(), device=dev)
     slots_a, slots_b = list(range(B)), list(range(B, 2 * B))
     frame_bytes = w * h
@@ -380,6 +383,10 @@ def run_ours(args):
                                     "working set per step)" % (B * n0 / 1e6,
                                                                  2 * B * 21e6 / 1e9),
                        "cluster_size": args.cluster,
+                       "estimate_kernel": ("cluster" if (args.cluster_kernel or args.cluster or
+                                                         args.weights or args.dmma_accum)
+                                           else "dataflow"),
+                       "weights": ["identity", "tukey_mad", "huber"][args.weights],
                        "parallelism": "independent sequences, %d per GPU, no comms" % B},
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": ms_e / K,
                     "h2d_bytes_per_step": B * n0, "d2h_bytes_per_step":
@@ -400,7 +407,7 @@ def run_ours(args):
             # bounded CPU sample of the same workload: the first `nseq` sequences, all K+W steps
             nseq = min(B, args.cpu_sequences)
             fr = host[:1 + W + K, :nseq].permute(1, 0, 2, 3).contiguous().numpy()
-            n, dt, poses = cpu_tracks(fr, 1)
+            n, dt, poses = cpu_tracks(fr, 1, weight_mode=args.weights)
             line["cpu_baseline"] = {
                 "value": n / dt, "unit": "tracks/s", "cores": 1, "kind": "port",
                 "sample": "%d sequences x %d frames of this workload (%d tracks, %.1f s), "
@@ -427,6 +434,10 @@ def main():
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per problem (0 = auto)")
     ap.add_argument("--dmma-accum", action="store_true",
                     help="A/B: Gram accumulator in fp64 DMMA fragments (slower; off by default)")
+    ap.add_argument("--cluster-kernel", action="store_true",
+                    help="A/B: one cluster per problem instead of the dataflow kernel")
+    ap.add_argument("--weights", type=int, default=0,
+                    help="residual weights: 0 identity (reference), 1 Tukey/MAD, 2 Huber")
     ap.add_argument("--cpu-sequences", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

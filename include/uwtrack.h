@@ -69,6 +69,9 @@ extern "C" {
  * m8n8k4) fragments per warp instead of 27 fp64 registers per thread.  Bit-identical results;
  * measured SLOWER on B200 (1.94 vs 1.19 ms per 128 problems), so it is off by default. */
 #define UWT_FLAG_DMMA_ACCUM 2u
+/* A/B switch: keep batches on the one-cluster-per-problem kernel instead of the persistent
+ * dataflow kernel (chunk tasks from a global ring) that batches of >= 24 problems use. */
+#define UWT_FLAG_CLUSTER_KERNEL 4u
 
 typedef struct uwt_tracker uwt_tracker;
 

@@ -243,6 +243,62 @@ def test_robust_weights_batch_and_rejections(oracle, pairs):
         make_tracker(calib, weight_mode=L.WEIGHT_TUKEY, flags=L.FLAG_DMMA_ACCUM)
 
 
+def test_dataflow_kernel_traces_match_oracle(oracle, pairs):
+    """Batches of 24 .. 295 problems run on the persistent dataflow kernel (chunk tasks from a global
+    ring): every per-sweep quantity of every problem must equal the oracle's, including problems
+    without candidate points (ARITHMETIC.md U2) and identical frames."""
+    import uw_slam_b200._lib as L
+    calib = "small"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    B = 40
+    prevs = [pairs(calib, s)[0] for s in range(B)]
+    curs = [pairs(calib, s)[1] for s in range(B)]
+    prevs[3] = np.full((h, w), 90, np.uint8)          # flat: no candidates on any level
+    curs[7] = prevs[7].copy()                         # identical frames
+    prevs[11] = prevs[11].copy()
+    prevs[11][: h // 2] = 17                          # half flat: fewer points, empty coarse rows
+    t = make_tracker(calib, max_frames=2 * B, flags=L.FLAG_TRACE)
+    fp = t.AddFrames(list(range(B)), np.stack(prevs))
+    fc = t.AddFrames(list(range(B, 2 * B)), np.stack(curs))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    init = np.tile(np.array([0, 0, 0, 1, 0, 0, 0], np.float32), (B, 1))
+    init[5] = oracle.se3_exp(np.array([1e-3, -2e-3, 1e-3, 2e-3, 1e-3, -1e-3], np.float32))
+    poses, stats = t.EstimatePose(fp, fc, init_poses=init, return_stats=True)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for s in range(B):
+        rp = oracle.FrameData(prevs[s])
+        rc = oracle.FrameData(curs[s], with_candidates=False)
+        opose, ostats, otrace = oracle.estimate_pose(p, rp, rc, init_pose=init[s])
+        assert_trace_equal(t.get_trace(s), otrace)
+        assert np.array_equal(poses[s], opose), s
+        assert list(stats[s].iterations)[:5] == list(ostats.iterations)[:5], s
+        assert list(stats[s].evaluations)[:5] == list(ostats.evaluations)[:5], s
+        assert list(stats[s].n_points)[:5] == list(ostats.n_points)[:5], s
+    t.close()
+
+
+def test_dataflow_and_cluster_kernels_agree_bitwise(pairs):
+    import uw_slam_b200._lib as L
+    calib = "tum_mono"
+    B = 32
+    prevs = np.stack([pairs(calib, s % 4)[0] for s in range(B)])
+    curs = np.stack([pairs(calib, (s * 7) % 5)[1] for s in range(B)])
+    out = []
+    for flags in (0, L.FLAG_CLUSTER_KERNEL):
+        t = make_tracker(calib, max_frames=2 * B, flags=flags)
+        fp = t.AddFrames(list(range(B)), prevs)
+        fc = t.AddFrames(list(range(B, 2 * B)), curs)
+        t.ApplyGradient(fp)
+        t.ObtainCandidatePoints(fp)
+        for rep in range(3):   # the ring and the control block are re-armed per launch
+            poses, stats = t.EstimatePose(fp, fc, return_stats=True)
+        out.append((poses, [list(s.evaluations) + list(s.n_points) for s in stats]))
+        t.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1]
+
+
 def test_dmma_accumulator_variant_matches_oracle(oracle, pairs):
     import uw_slam_b200._lib as L
     prev, cur = pairs("tum", 5)
@@ -273,7 +329,7 @@ def test_batch_of_independent_pairs(oracle, pairs):
         rp, rc = oracle.FrameData(prevs[s]), oracle.FrameData(curs[s], with_candidates=False)
         opose, _, _ = oracle.estimate_pose(p, rp, rc)
         assert np.array_equal(poses[s], opose), s
-    assert t.launch_count() == 2 + 1 + 3 + 1
+    assert t.launch_count() == 2 + 1 + 3 + 2   # estimate = ring init + dataflow kernel
     t.close()
 
 

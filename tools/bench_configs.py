@@ -102,7 +102,8 @@ def batch8192(args, torch, dist, rank, local_rank, world):
     lo, hi = total * rank // world, total * (rank + 1) // world   # pair i -> GPU floor(i*G/B)
     mine = hi - lo
     chunk = min(args.chunk, mine)
-    t = make_tracker(calib, local_rank, max_frames=2 * chunk)
+    t = make_tracker(calib, local_rank, max_frames=2 * chunk, flags=args.flags,
+                     weight_mode=args.weights)
     # resident inputs: all of this rank's pairs, rendered on the device
     prev = torch.empty((mine, h, w), dtype=torch.uint8, device=dev)
     cur = torch.empty_like(prev)
@@ -135,11 +136,12 @@ def batch8192(args, torch, dist, rank, local_rank, world):
     res = {"metric": "pose-tracks/sec, 8192 independent 640x480 pairs (pyramids x2, gradient, "
                      "candidates, estimate per pair; inputs resident in HBM)",
            "value": total / float(dt.item()), "unit": "tracks/s", "pairs": total,
-           "n_gpus": world, "scaling": "strong", "chunk": chunk}
+           "n_gpus": world, "scaling": "strong", "chunk": chunk, "flags": args.flags,
+           "weights": ["identity", "tukey_mad", "huber"][args.weights]}
     if rank == 0:
         # spot-check 4 pairs against the oracle
         from oracle import uw_oracle as O
-        p = O.default_params(*synth.CALIB[calib])
+        p = O.default_params(*synth.CALIB[calib], weight_mode=args.weights)
         same = True
         for i in [0, 1, mine // 2, mine - 1]:
             a, b = prev[i].cpu().numpy(), cur[i].cpu().numpy()
@@ -211,6 +213,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="uwt_config.flags (4 = cluster kernel)")
+    ap.add_argument("--weights", type=int, default=0, help="0 identity, 1 Tukey/MAD, 2 Huber")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist

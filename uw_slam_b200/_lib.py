@@ -6,12 +6,14 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libuwtrack.so")
+# UWT_LIBRARY: development knob to A/B a differently built libuwtrack (tools/ab_variants.sh)
+SO_PATH = os.environ.get("UWT_LIBRARY") or os.path.join(HERE, "libuwtrack.so")
 MAX_LEVELS = 7
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
 SOLVE_LU, SOLVE_INVERSE = 0, 1
 FLAG_TRACE = 1
 FLAG_DMMA_ACCUM = 2
+FLAG_CLUSTER_KERNEL = 4
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 

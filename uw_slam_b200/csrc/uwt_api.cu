@@ -21,6 +21,12 @@ using namespace uwt;
 namespace {
 
 constexpr int kRing = 8;
+// The dataflow estimate kernel serves the batch sizes where one-cluster-per-problem suffers from
+// wave quantisation and per-sweep barriers (measured on B200, 128 problems at 1280x1024: 0.96 vs
+// 1.03 ms).  Fewer problems: the 16-CTA cluster has the lower latency; from 2 CTAs per SM upwards
+// single-CTA problems balance by themselves (8192 x 640x480: 260 k vs 244 k tracks/s).
+constexpr int kFlowMinProblems = 24;
+constexpr int kFlowMaxProblems = 2 * 148;
 constexpr int kTraceProblems = 64;
 
 thread_local std::string g_create_error;
@@ -77,6 +83,10 @@ struct uwt_tracker {
   // private single-rank instance of the fused kernel: whole-GPU path of ONE large problem
   ShardFused* d_fused_self = nullptr;
   ShardMailbox* d_mailbox_self = nullptr;
+  void* d_flow_ws = nullptr;          // workspace of the batched dataflow estimate kernel
+  size_t flow_ws_bytes = 0;
+  int* h_flow_ctl = nullptr;          // pinned copy of its control block {head, tail, active, error}
+  bool flow_last = false;
   float* d_out_poses = nullptr;
   uwt_track_stats* d_stats = nullptr;
   float* h_out_poses = nullptr;       // pinned
@@ -284,6 +294,8 @@ void destroy_impl(uwt_tracker* t) {
   cudaFree(t->d_shard_done);
   if (t->h_shard_done) cudaFreeHost(t->h_shard_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  cudaFree(t->d_flow_ws);
+  if (t->h_flow_ctl) cudaFreeHost(t->h_flow_ctl);
   cudaFree(t->d_out_poses);
   cudaFree(t->d_stats);
   cudaFree(t->d_trace);
@@ -438,6 +450,7 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   CREATE_CUDA(cudaMalloc(&t->d_stats, sizeof(uwt_track_stats) * F));
   CREATE_CUDA(cudaHostAlloc(&t->h_out_poses, sizeof(float) * 7 * F, cudaHostAllocDefault));
   CREATE_CUDA(cudaHostAlloc(&t->h_stats, sizeof(uwt_track_stats) * F, cudaHostAllocDefault));
+  CREATE_CUDA(cudaHostAlloc(&t->h_flow_ctl, sizeof(int) * 4, cudaHostAllocDefault));
   if (c.flags & UWT_FLAG_TRACE) {
     t->trace_cap = (c.first_level - c.last_level + 1) * c.max_iterations;
     CREATE_CUDA(cudaMalloc(&t->d_trace, sizeof(uwt_iter_trace) * t->trace_cap * kTraceProblems));
@@ -761,6 +774,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
       if ((rc = release(t, r))) return rc;
       t->last_n = 1;
       t->shard_active = false;
+      t->flow_last = false;
       return UWT_OK;
     }
   }
@@ -783,10 +797,30 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   io.trace_count = tracing ? t->d_trace_count : nullptr;
   io.trace_cap = t->trace_cap;
   int cluster = pick_cluster(t, n);
+  // Batches: the persistent dataflow kernel (chunk tasks, no per-sweep barriers, no tail of
+  // unequal problems).  Few problems, robust weights, the DMMA A/B variant and an explicit
+  // cluster size stay on the cluster kernel.
+  const bool use_flow = n >= kFlowMinProblems && n < kFlowMaxProblems &&
+                        t->cfg.cluster_size == 0 &&
+                        t->cfg.weight_mode == UWT_WEIGHT_IDENTITY &&
+                        !(t->cfg.flags & (UWT_FLAG_DMMA_ACCUM | UWT_FLAG_CLUSTER_KERNEL));
+  if (use_flow) {
+    const size_t need = flow_workspace_bytes(t->geom, n);
+    if (need > t->flow_ws_bytes) {
+      UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+      cudaFree(t->d_flow_ws);
+      t->d_flow_ws = nullptr;
+      t->flow_ws_bytes = 0;
+      UWT_CUDA(t, cudaMalloc(&t->d_flow_ws, need));
+      t->flow_ws_bytes = need;
+    }
+  }
   ProfSpan span(t, UWT_K_ESTIMATE);
   const int variant = (t->cfg.flags & UWT_FLAG_DMMA_ACCUM) ? UWT_EST_MMA : UWT_EST_REGISTERS;
-  int k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream, variant);
-  while (k < 0 && cluster > 1) {  // a 16-CTA cluster may not be schedulable on every part
+  int k = -2;
+  if (use_flow) k = launch_estimate_flow(t->geom, t->pools, n, io, t->d_flow_ws, t->stream);
+  if (k == -2) k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream, variant);
+  while (k < 0 && cluster > 1 && !use_flow) {  // a 16-CTA cluster may not be schedulable on every part
     cudaGetLastError();
     cluster /= 2;
     t->max_cluster = cluster;
@@ -800,6 +834,10 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
                               cudaMemcpyDeviceToHost, t->stream));
   UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, t->d_stats, sizeof(uwt_track_stats) * n,
                               cudaMemcpyDeviceToHost, t->stream));
+  t->flow_last = use_flow && k > 0;
+  if (t->flow_last)
+    UWT_CUDA(t, cudaMemcpyAsync(t->h_flow_ctl, t->d_flow_ws, sizeof(int) * 4,
+                                cudaMemcpyDeviceToHost, t->stream));
   UWT_CUDA(t, cudaEventRecord(t->poses_ready, t->stream));
   if ((rc = release(t, r))) return rc;
   t->last_n = n;
@@ -812,6 +850,9 @@ int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* s
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   // waits for the estimate + its D2H only, not for work enqueued after it
   UWT_CUDA(t, cudaEventSynchronize(t->poses_ready));
+  if (t->flow_last && (t->h_flow_ctl[3] != 0 || t->h_flow_ctl[2] != 0))
+    return fail(t, UWT_E_CUDA, "dataflow estimate kernel did not complete (error %d, %d problems "
+                "unfinished)", t->h_flow_ctl[3], t->h_flow_ctl[2]);
   if (out_poses7) std::memcpy(out_poses7, t->h_out_poses, sizeof(float) * 7 * n);
   if (stats) std::memcpy(stats, t->h_stats, sizeof(uwt_track_stats) * n);
   return UWT_OK;

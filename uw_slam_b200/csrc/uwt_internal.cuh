@@ -129,6 +129,10 @@ constexpr int UWT_EST_MMA = 0;        // Gram accumulator in fp64 tensor-core fr
 constexpr int UWT_EST_REGISTERS = 1;  // 27 fp64 register accumulators per thread
 int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
                     cudaStream_t st, int variant);
+// persistent dataflow form for batches (chunk tasks from a global ring, no barriers)
+size_t flow_workspace_bytes(const Geom& g, int nprob);
+int launch_estimate_flow(const Geom& g, const Pools& p, int n, const EstimateIO& io,
+                         void* workspace, cudaStream_t st);
 int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, double* partials,
                             double* out32, int grid, cudaStream_t stream);
 int launch_shard_update(const Geom& g, const Pools& p, ShardState* st, const double* sums32,
