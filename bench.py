@@ -393,7 +393,10 @@ def run_ours(args):
                     B * (7 * 4 + 4 * 4 * 7)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "estimate_kernel", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": ("estimate_kernel (cluster)"
+                                    if (args.cluster_kernel or args.cluster or args.weights or
+                                        args.dmma_accum) else "estimate_flow_kernel"),
+                         "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(B),
                          "algorithmic_bytes_per_launch": bytes_per_launch,
