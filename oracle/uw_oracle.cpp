@@ -465,6 +465,15 @@ void uwo_se3_scale_level(const float* pose7, float* out7) {
   pose_to7(se3_scale_level(pose_from7(pose7)), out7);
 }
 
+void uwo_chain_pose(const float* previous7, const float* rigid7, float scale, float* out7) {
+  // Visualizer.cpp:303-309: t_TUM = 40 * translation; SE3(unit_quaternion, t_TUM) normalises
+  Pose cur;
+  const float len = std::sqrt(quat_sqnorm(rigid7));
+  for (int i = 0; i < 4; ++i) cur.q[i] = rigid7[i] / len;
+  for (int i = 0; i < 3; ++i) cur.t[i] = scale * rigid7[4 + i];
+  pose_to7(se3_mul(pose_from7(previous7), cur), out7);  // Visualizer.cpp:311
+}
+
 int uwo_lu_solve6(const float* A36, const float* b6, float* x6) {
   float A[36], B[6];
   std::memcpy(A, A36, sizeof(A));

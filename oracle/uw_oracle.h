@@ -111,6 +111,10 @@ void uwo_tukey_weights(const float* v, int n, float* w);
 /* Huber weights (north-star option; docs/ARITHMETIC.md R4). */
 void uwo_huber_weights(const float* v, int n, float delta, float* w);
 
+/* Visualizer::UpdateMessages pose composition (Visualizer.cpp:303-325): current = SE3(q, scale*t)
+ * (normalising constructor, se3.hpp:446-448), out = previous * current. */
+void uwo_chain_pose(const float* previous7, const float* rigid7, float scale, float* out7);
+
 /* cv::solve / cv::invert (DECOMP_LU) on 6x6 f32.  Return 0 if singular. */
 int uwo_lu_solve6(const float* A36, const float* b6, float* x6);
 int uwo_lu_invert6(const float* A36, float* Ainv36);

@@ -269,6 +269,17 @@ def se3_mul(a7, b7):
     return o
 
 
+def chain_pose(prev7, rigid7, scale=40.0):
+    a = np.ascontiguousarray(prev7, np.float32)
+    b = np.ascontiguousarray(rigid7, np.float32)
+    o = np.empty(7, np.float32)
+    f = lib().uwo_chain_pose
+    f.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+    f.restype = None
+    f(_p(a, C.c_float), _p(b, C.c_float), float(scale), _p(o, C.c_float))
+    return o
+
+
 def se3_matrix(p7):
     p7 = np.ascontiguousarray(p7, np.float32)
     o = np.empty(16, np.float32)
