@@ -97,4 +97,5 @@ def test_tum_ground_truth_reader(tmp_path):
     tr = T.Trajectory()
     tr.Update(np.array([0, 0, 0, 1, 0.01, 0, 0], np.float32))
     tr.WriteTUM(str(tmp_path / "o.txt"))
-    assert (tmp_path / "o.txt").read_text().split()[1] == "0.400000006"
+    assert (tmp_path / "o.txt").read_text().split()[1] == \
+        "%.9g" % (np.float32(40) * np.float32(0.01))   # the reference's x40 translation scale
