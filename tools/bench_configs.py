@@ -18,6 +18,9 @@ import time
 
 import numpy as np
 
+# keep stdout for the one JSON line: NCCL banners / debug output go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 

@@ -1152,8 +1152,23 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
   if (cnt > capacity_rows)
     return fail(t, UWT_E_INVALID, "capacity %d < %d candidates", capacity_rows, cnt);
   if (cnt == 0) return UWT_OK;
-  std::vector<uint32_t> xy(cnt);
   const LevelGeom& L = t->geom.lv[level];
+  if (L.rec_off >= 0) {
+    // optimised levels keep only the packed records; (x, y) are their low 24 bits
+    std::vector<uint64_t> rec(cnt);
+    UWT_CUDA(t, cudaMemcpyAsync(rec.data(),
+                                t->pools.rec + (size_t)slot * t->geom.rec_elems + L.rec_off,
+                                sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, t->stream));
+    UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+    for (int i = 0; i < cnt; ++i) {  // candidatePoints_ rows, Tracker.cpp:1351-1355
+      pts4[i * 4 + 0] = (float)(rec[i] & 0xFFFu);
+      pts4[i * 4 + 1] = (float)((rec[i] >> 12) & 0xFFFu);
+      pts4[i * 4 + 2] = 1.0f;
+      pts4[i * 4 + 3] = 1.0f;
+    }
+    return UWT_OK;
+  }
+  std::vector<uint32_t> xy(cnt);
   UWT_CUDA(t, cudaMemcpyAsync(xy.data(),
                               t->pools.cand_xy + (size_t)slot * t->geom.cand_elems + L.cand_off,
                               sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, t->stream));

@@ -299,11 +299,14 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
         const uint32_t b = __ballot_sync(0xffffffffu, sel);
         if (sel) {
           const uint32_t o = base + __popc(b & lt_mask);
-          xy[o] = (uint32_t)x | ((uint32_t)y << 16);
           if (has_rec) {
+            // a record carries (x, y) itself: the plain (x, y) list is kept only for the levels
+            // EstimatePose never optimises (read-back of candidatePoints_ decodes either form)
             int gx, gy, i1;
             scharr_from_tile(ti, x0, y0, x, y, gx, gy, i1);
             rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
+          } else {
+            xy[o] = (uint32_t)x | ((uint32_t)y << 16);
           }
         }
         base += __popc(b);

@@ -224,7 +224,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 constexpr int kHaloX = 16;                               // 16-byte aligned halo
 constexpr int kTileRowBytes = kGradTileW + 2 * kHaloX;   // 160
-constexpr int kTileRows = kGradTileH + 2;                // 34
+constexpr int kTileRows = kGradTileH + 2;
 
 // dp4a with unsigned pixel bytes and signed stencil weights (SASS: IDP.4A.U8.S8)
 __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {
@@ -324,20 +324,21 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
     __syncthreads();
   }
 
-  // ---- compute: warp = 4 rows, lane = 4 pixels; 5 dp4a per pixel (3 for gx, 2 for gy) ----
+  // ---- compute: warp = kGradTileH / 8 rows, lane = 4 pixels; 5 dp4a per pixel (3 gx, 2 gy) ----
   const int lane = t & 31, wy = t >> 5;
   const int xg = x0 + lane * 4;
   const int sx = kHaloX + lane * 4;
   uint32_t gsum = 0;
-  const int ybase = y0 + wy * 4;
+  constexpr int kRowsPerWarp = kGradTileH / 8;
+  const int ybase = y0 + wy * kRowsPerWarp;
   if (xg < L.w && ybase < L.h) {
     const int nvalid = min(4, L.w - xg);
     const uint32_t vmask = nvalid == 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-    const uint8_t* trow = &tile[wy * 4][0];  // tile row of image row ybase - 1
+    const uint8_t* trow = &tile[wy * kRowsPerWarp][0];  // tile row of image row ybase - 1
     RowWin top = row_windows(trow, sx);
     RowWin mid = row_windows(trow + kTileRowBytes, sx);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kRowsPerWarp; ++j) {
       const int y = ybase + j;
       if (y >= L.h) break;
       const RowWin bot = row_windows(trow + (j + 2) * kTileRowBytes, sx);

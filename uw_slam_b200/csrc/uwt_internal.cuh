@@ -9,12 +9,19 @@ namespace uwt {
 
 constexpr int kMaxLevels = UWT_MAX_LEVELS;
 
-// Gradient tile (K2): 128 x 32 pixels, staged with a 16-byte-aligned halo by cp.async.bulk.
+// Gradient tile (K2): 128 x kGradTileH pixels, staged with a 16-byte-aligned halo by
+// cp.async.bulk; 8 warps x (kGradTileH / 8) rows.
 constexpr int kGradTileW = 128;
-constexpr int kGradTileH = 32;
+#ifndef UWT_GRAD_TILE_H
+#define UWT_GRAD_TILE_H 128
+#endif
+constexpr int kGradTileH = UWT_GRAD_TILE_H;
 // Candidate compaction (K3): one CTA owns a 128-column strip x kSegRows rows.
 constexpr int kStripW = 128;
-constexpr int kSegRows = 64;
+#ifndef UWT_SEG_ROWS
+#define UWT_SEG_ROWS 64
+#endif
+constexpr int kSegRows = UWT_SEG_ROWS;  // <= 255: the count kernel packs per-column counts in bytes
 // Pyramid tile (K1): 64 x 64 level-0 pixels -> 32x32, 16x16, 8x8, 4x4, 2x2, 1x1.
 constexpr int kPyrTile = 64;
 
