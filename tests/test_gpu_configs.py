@@ -1,0 +1,120 @@
+"""GPU parity over the configuration space of the C ABI (levels, optimised range, thresholds,
+iteration limits, frame sizes up to the maximum): everything against the oracle with the same
+parameters, bit for bit."""
+import numpy as np
+import pytest
+
+from uw_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_case(oracle, w, h, seed, levels, first, last, batch=1, **cfg):
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    fx, fy, cx, cy = 0.8 * w, 0.82 * w, w / 2 - 0.5, h / 2 - 0.5
+    synth.CALIB["_cfg"] = (w, h, fx, fy, cx, cy)
+    pairs = [synth.render_pair("_cfg", seed + i)[:2] for i in range(batch)]
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=2 * batch, levels=levels, first_level=first, last_level=last,
+                        flags=L.FLAG_TRACE, **cfg)
+    fp = t.AddFrames(list(range(batch)), np.stack([p[0] for p in pairs]))
+    fc = t.AddFrames(list(range(batch, 2 * batch)), np.stack([p[1] for p in pairs]))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    poses, stats = t.EstimatePose(fp, fc, return_stats=True)
+    okw = {k: v for k, v in cfg.items() if k in ("max_iterations", "epsilon", "residual_scale",
+                                                 "gradient_threshold", "solve_mode",
+                                                 "weight_mode", "huber_delta")}
+    p = oracle.default_params(w, h, fx, fy, cx, cy, levels=levels, first_level=first,
+                              last_level=last, **okw)
+    thr = cfg.get("gradient_threshold", 20.0)
+    for i in range(batch):
+        rp = oracle.FrameData(pairs[i][0], levels=levels, gradient_threshold=thr)
+        rc = oracle.FrameData(pairs[i][1], levels=levels, with_candidates=False)
+        if i == 0:
+            for lvl in range(levels):
+                assert np.array_equal(fp[0].image(lvl), rp.images[lvl]), lvl
+                gx, gy, g = fp[0].gradients(lvl)
+                assert np.array_equal(gx, rp.gx[lvl]) and np.array_equal(gy, rp.gy[lvl]), lvl
+                assert np.array_equal(g, rp.g[lvl]), lvl
+                assert np.array_equal(fp[0].candidatePoints(lvl), rp.cand[lvl]), lvl
+        opose, ostats, otrace = oracle.estimate_pose(p, rp, rc, trace_cap=1024)
+        if batch <= 64:
+            tr = t.get_trace(i, cap=1024)
+            assert [(a.level, a.k, a.n_valid, a.broke, a.sum_r2) for a in tr] == \
+                [(b.level, b.k, b.n_valid, b.broke, b.sum_r2) for b in otrace], i
+            for a, b in zip(tr, otrace):
+                assert np.array_equal(np.array(a.A[:]), np.array(b.A[:])), (i, b.level, b.k)
+                assert np.array_equal(np.array(a.delta[:]), np.array(b.delta[:])), (i, b.level, b.k)
+        assert np.array_equal(poses[i], opose), i
+        assert list(stats[i].iterations)[:levels] == list(ostats.iterations)[:levels]
+    t.close()
+
+
+@pytest.mark.parametrize("levels,first,last", [(1, 0, 0), (2, 1, 0), (3, 2, 0), (3, 2, 2),
+                                               (5, 4, 0), (5, 3, 2), (6, 5, 1), (7, 6, 3)])
+def test_level_configurations(oracle, levels, first, last):
+    # 320x256 is divisible by 2^6; level 0 can be optimised too (records on level 0)
+    run_case(oracle, 320, 256, 11, levels, first, last)
+
+
+@pytest.mark.parametrize("cfg", [dict(max_iterations=1), dict(max_iterations=3),
+                                 dict(epsilon=5.0), dict(residual_scale=12.5),
+                                 dict(residual_scale=1.0, max_iterations=8),
+                                 dict(gradient_threshold=5.0), dict(gradient_threshold=60.5),
+                                 dict(gradient_threshold=400.0),   # nothing passes: U2 everywhere
+                                 dict(solve_mode=1, weight_mode=1),
+                                 dict(weight_mode=2, huber_delta=3.0, residual_scale=20.0)])
+def test_parameter_variations(oracle, cfg):
+    run_case(oracle, 160, 128, 5, 5, 4, 1, **cfg)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(levels=4, first=3, last=0)])
+def test_dataflow_kernel_configurations(oracle, cfg):
+    # 32 problems -> the dataflow kernel; non-default level ranges included
+    run_case(oracle, 160, 128, 40, cfg.get("levels", 5), cfg.get("first", 4), cfg.get("last", 1),
+             batch=32)
+
+
+@pytest.mark.parametrize("w,h", [(4096, 4096), (4096, 16), (16, 4096), (1936, 1216)])
+def test_extreme_frame_sizes(oracle, w, h):
+    """The largest supported frame (12-bit record coordinates), degenerate strips and a size
+    that leaves ragged tiles in every kernel."""
+    import uw_slam_b200 as U
+    rng = np.random.default_rng(w + h)
+    levels = 5 if min(w, h) >= 32 else 1
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    # smooth it a little so that candidates are a realistic fraction
+    img = ((img.astype(np.uint16) + np.roll(img, 1, 0) + np.roll(img, 1, 1) +
+            np.roll(img, 2, 1)) // 4).astype(np.uint8)
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, w, w, w / 2, h / 2).GetK(),
+                        max_frames=1, levels=levels, first_level=levels - 1,
+                        last_level=min(1, levels - 1))
+    f = t.AddFrames([0], img)[0]
+    t.ApplyGradient(f)
+    t.ObtainCandidatePoints(f)
+    ref = oracle.FrameData(img, levels=levels)
+    for lvl in range(levels):
+        assert np.array_equal(f.image(lvl), ref.images[lvl]), lvl
+        gx, gy, g = f.gradients(lvl)
+        assert np.array_equal(gx, ref.gx[lvl]) and np.array_equal(gy, ref.gy[lvl]), lvl
+        assert np.array_equal(g, ref.g[lvl]), lvl
+        assert np.array_equal(f.candidatePoints(lvl), ref.cand[lvl]), lvl
+    t.close()
+
+
+def test_rejected_configurations():
+    import uw_slam_b200 as U
+    K = U.CameraModel.from_intrinsics(640, 480, 500, 500, 320, 240).GetK()
+    for bad in (dict(width=4112, height=480), dict(width=648, height=480),   # > 4096, w % 16
+                dict(width=640, height=488),                                   # h % 16
+                dict(levels=0), dict(levels=8), dict(first_level=5), dict(last_level=-1),
+                dict(first_level=1, last_level=2), dict(max_iterations=0), dict(max_frames=0),
+                dict(solve_mode=2), dict(cluster_size=3), dict(device=99)):
+        cfg = dict(bad)
+        w, h = cfg.pop("width", 640), cfg.pop("height", 480)
+        with pytest.raises(U.UwtError):
+            U.Tracker(False).InitializePyramid(w, h, K, **cfg)
