@@ -462,3 +462,32 @@ def test_fused_sharded_two_emulated_ranks_match_oracle(oracle, pairs):
         assert np.array_equal(poses[0], opose)
     for t in ts:
         t.close()
+
+
+def test_two_devices_in_one_process(oracle, pairs):
+    """Handles on different GPUs of one process (function attributes are per device): both must
+    track, on every estimate kernel.  Needs >= 2 visible GPUs."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    calib = "tum"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    B = 32
+    prevs = np.stack([pairs(calib, s % 3)[0] for s in range(B)])
+    curs = np.stack([pairs(calib, s % 3)[1] for s in range(B)])
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    ref = [oracle.estimate_pose(p, oracle.FrameData(prevs[s]),
+                                oracle.FrameData(curs[s], with_candidates=False))[0]
+           for s in range(3)]
+    for dev in (1, 0):
+        t = make_tracker(calib, max_frames=2 * B, device=dev)
+        fp = t.AddFrames(list(range(B)), prevs)
+        fc = t.AddFrames(list(range(B, 2 * B)), curs)
+        t.ApplyGradient(fp)
+        t.ObtainCandidatePoints(fp)
+        poses = t.EstimatePose(fp, fc)                       # dataflow kernel
+        one = t.EstimatePose(fp[:1], fc[:1])                 # 16-CTA cluster kernel
+        for s in range(B):
+            assert np.array_equal(poses[s], ref[s % 3]), (dev, s)
+        assert np.array_equal(one[0], ref[0]), dev
+        t.close()

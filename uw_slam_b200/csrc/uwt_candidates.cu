@@ -320,7 +320,7 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   // persistent grids: a multiple of the 148 SMs, as many CTAs per SM as the double-buffered
   // tiles allow; small jobs get one CTA per work item
   const long long total = (long long)g.warp_items_total * n;
-  static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;
+  static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;  // same for every device of a box
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
