@@ -39,6 +39,42 @@ ROT = TRANS = 5e-3  # per-frame motion magnitude
 BYTES_PER_POINT = 10  # (x,y) 4 B + I1 1 B + gx,gy 4 B + I2 gather 1 B
 
 
+def claim_stdout():
+    """NCCL and friends print banners on fd 1; the contract is ONE JSON line on stdout.  Point
+    fd 1 at stderr for the whole run and return a file on the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned host buffer is touched,
+    so the frames every step uploads live in memory local to that GPU's PCIe root (first-touch).
+    With 8 ranks on a two-socket host the H2D streams otherwise cross the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # nvml pads the domain to 8 hex digits
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def dist_env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
@@ -209,7 +245,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -220,6 +256,7 @@ def run_ours(args):
     from uw_slam_b200 import _lib as L
 
     rank, local_rank, world = dist_env()
+    numa_node = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -390,6 +427,7 @@ def run_ours(args):
                                                          args.weights or args.dmma_accum)
                                            else "dataflow"),
                        "weights": ["identity", "tukey_mad", "huber"][args.weights],
+                       "host_numa_node_of_rank0": numa_node,
                        "parallelism": "independent sequences, %d per GPU, no comms" % B},
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": ms_e / K,
                     "h2d_bytes_per_step": B * n0, "d2h_bytes_per_step":
@@ -422,7 +460,7 @@ def run_ours(args):
             gpu_last = stats_acc[-1][0]
             same = all(np.array_equal(poses[s][-1], gpu_last[s]) for s in range(nseq))
             line["cpu_baseline"]["gpu_pose_bit_identical_on_sample"] = bool(same)
-        print(json.dumps(line))
+        print(json.dumps(line), file=args.out, flush=True)
     t.close()
     if world > 1:
         dist.barrier()
@@ -447,6 +485,7 @@ def main():
     ap.add_argument("--cpu-sequences", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.out = claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="uwt_config.flags (4 = cluster kernel)")
     ap.add_argument("--weights", type=int, default=0, help="0 identity, 1 Tukey/MAD, 2 Huber")
     args = ap.parse_args()
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")   # banners (NCCL ...) go to stderr, the JSON here
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank, local_rank, world = env()
@@ -229,7 +232,7 @@ def main():
         args, torch, dist, rank, local_rank, world)
     res["workload"] = args.workload
     if rank == 0:
-        print(json.dumps(res))
+        print(json.dumps(res), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
