@@ -276,7 +276,8 @@ def run_ours(args):
     t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
                         max_frames=2 * B, device=local_rank, cluster_size=args.cluster,
                         flags=(L.FLAG_DMMA_ACCUM if args.dmma_accum else 0) |
-                        (L.FLAG_CLUSTER_KERNEL if args.cluster_kernel else 0),
+                        (L.FLAG_CLUSTER_KERNEL if args.cluster_kernel else 0) |
+                        (L.FLAG_LAZY_LEVELS if args.lazy_levels else 0),
                         weight_mode=args.weights)
     stream = torch.cuda.ExternalStream(t.stream_ptr(), device=dev)
     slots_a, slots_b = list(range(B)), list(range(B, 2 * B))
@@ -427,6 +428,7 @@ def run_ours(args):
                                                          args.weights or args.dmma_accum)
                                            else "dataflow"),
                        "weights": ["identity", "tukey_mad", "huber"][args.weights],
+                       "lazy_levels": bool(args.lazy_levels),
                        "host_numa_node_of_rank0": numa_node,
                        "parallelism": "independent sequences, %d per GPU, no comms" % B},
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": ms_e / K,
@@ -480,6 +482,9 @@ def main():
                     help="A/B: Gram accumulator in fp64 DMMA fragments (slower; off by default)")
     ap.add_argument("--cluster-kernel", action="store_true",
                     help="A/B: one cluster per problem instead of the dataflow kernel")
+    ap.add_argument("--lazy-levels", action="store_true",
+                    help="opt-in UWT_FLAG_LAZY_LEVELS: gradient/candidates only on the optimised "
+                         "levels (the default does all levels, like the reference)")
     ap.add_argument("--weights", type=int, default=0,
                     help="residual weights: 0 identity (reference), 1 Tukey/MAD, 2 Huber")
     ap.add_argument("--cpu-sequences", type=int, default=8)

@@ -72,6 +72,12 @@ extern "C" {
 /* A/B switch: keep batches on the one-cluster-per-problem kernel instead of the persistent
  * dataflow kernel (chunk tasks from a global ring) that batches of >= 24 problems use. */
 #define UWT_FLAG_CLUSTER_KERNEL 4u
+/* Opt-in: uwt_apply_gradient / uwt_select_candidates work only on the levels uwt_estimate_pose
+ * optimises ([last_level, first_level]); gradient_ / candidatePoints_ of the other levels (level 0
+ * by default: 75 % of the pixels, never read by Tracker::EstimatePose, src/Tracker.cpp:389) are
+ * materialised by the same kernels when a read-back accessor asks for them.  Every result is
+ * identical to the default (eager) mode, which does what the reference does on all levels. */
+#define UWT_FLAG_LAZY_LEVELS 8u
 
 typedef struct uwt_tracker uwt_tracker;
 

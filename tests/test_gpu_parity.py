@@ -491,3 +491,36 @@ def test_two_devices_in_one_process(oracle, pairs):
             assert np.array_equal(poses[s], ref[s % 3]), (dev, s)
         assert np.array_equal(one[0], ref[0]), dev
         t.close()
+
+
+def test_lazy_levels_flag_is_observationally_identical(oracle, pairs):
+    """UWT_FLAG_LAZY_LEVELS: gradient / candidates only on the optimised levels; the other levels
+    appear on read-back, with the values the eager mode (and the oracle) has."""
+    import uw_slam_b200._lib as L
+    calib = "euroc"
+    prev, cur = pairs(calib, 6)
+    ref = oracle.FrameData(prev)
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    opose = oracle.estimate_pose(oracle.default_params(w, h, fx, fy, cx, cy), ref,
+                                 oracle.FrameData(cur, with_candidates=False))[0]
+    t = make_tracker(calib, flags=L.FLAG_LAZY_LEVELS)
+    fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    n0 = t.launch_count()
+    assert np.array_equal(t.EstimatePose(fp, fc)[0], opose)
+    # optimised levels are there without extra work ...
+    for lvl in (1, 4):
+        assert np.array_equal(fp.candidatePoints(lvl), ref.cand[lvl])
+        assert np.array_equal(fp.gradients(lvl)[2], ref.g[lvl])
+    # ... level 0 is materialised on demand (gradient image, then the candidate list)
+    n1 = t.launch_count()
+    gx, gy, g = fp.gradients(0)
+    assert np.array_equal(g, ref.g[0]) and np.array_equal(gx, ref.gx[0])
+    assert np.array_equal(fp.candidatePoints(0), ref.cand[0])
+    assert t.launch_count() > n1 and n1 > n0
+    # nothing changed for the tracker
+    assert np.array_equal(t.EstimatePose(fp, fc)[0], opose)
+    for lvl in range(5):
+        assert np.array_equal(fp.candidatePoints(lvl), ref.cand[lvl])
+    t.close()

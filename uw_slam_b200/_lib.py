@@ -14,6 +14,7 @@ SOLVE_LU, SOLVE_INVERSE = 0, 1
 FLAG_TRACE = 1
 FLAG_DMMA_ACCUM = 2
 FLAG_CLUSTER_KERNEL = 4
+FLAG_LAZY_LEVELS = 8
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 

@@ -33,6 +33,9 @@ thread_local std::string g_create_error;
 
 struct SlotState {
   bool pyramid = false, gradient = false, candidates = false;
+  // UWT_FLAG_LAZY_LEVELS: gradient / candidates exist on the optimised levels only until a
+  // read-back asks for another level (then all levels are materialised)
+  bool gradient_all = false, candidates_all = false;
 };
 
 struct ArgRegion {
@@ -552,7 +555,7 @@ static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t
   for (int i = 0; i < n; ++i) {
     SlotState& s = t->slots[slots[i]];
     s.pyramid = true;
-    s.gradient = s.candidates = false;
+    s.gradient = s.candidates = s.gradient_all = s.candidates_all = false;
   }
   return UWT_OK;
 }
@@ -669,7 +672,10 @@ int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
   ProfSpan span(t, UWT_K_GRADIENT);
-  const int k = launch_gradient(t->geom, t->pools, n, r->d_int, t->stream);
+  const bool lazy = (t->cfg.flags & UWT_FLAG_LAZY_LEVELS) != 0;
+  const LevelRange lr = lazy ? level_range(t->geom, t->cfg.last_level, t->cfg.first_level)
+                             : level_range(t->geom, 0, t->geom.levels - 1);
+  const int k = launch_gradient(t->geom, t->pools, n, r->d_int, t->stream, lr);
   span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "gradient kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
@@ -677,7 +683,8 @@ int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {
   if ((rc = release(t, r))) return rc;
   for (int i = 0; i < n; ++i) {
     t->slots[slots[i]].gradient = true;
-    t->slots[slots[i]].candidates = false;
+    t->slots[slots[i]].gradient_all = !lazy;
+    t->slots[slots[i]].candidates = t->slots[slots[i]].candidates_all = false;
   }
   return UWT_OK;
 }
@@ -693,13 +700,19 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
   ProfSpan span(t, UWT_K_CANDIDATES);
-  const int k = launch_candidates(t->geom, t->pools, n, r->d_int, t->stream);
+  const bool lazy = (t->cfg.flags & UWT_FLAG_LAZY_LEVELS) != 0;
+  const LevelRange lr = lazy ? level_range(t->geom, t->cfg.last_level, t->cfg.first_level)
+                             : level_range(t->geom, 0, t->geom.levels - 1);
+  const int k = launch_candidates(t->geom, t->pools, n, r->d_int, t->stream, lr);
   span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "candidate kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
   t->launches += k;
   if ((rc = release(t, r))) return rc;
-  for (int i = 0; i < n; ++i) t->slots[slots[i]].candidates = true;
+  for (int i = 0; i < n; ++i) {
+    t->slots[slots[i]].candidates = true;
+    t->slots[slots[i]].candidates_all = !lazy;
+  }
   return UWT_OK;
 }
 
@@ -1070,6 +1083,37 @@ int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7
   return UWT_OK;
 }
 
+// UWT_FLAG_LAZY_LEVELS: a read-back of a level outside [last_level, first_level] materialises
+// gradient (and, if they were selected, candidates) of ALL levels of that slot, with the same
+// kernels -- so every accessor returns exactly what the eager mode would.
+static int complete_levels(uwt_tracker* t, int slot, int level, bool need_candidates) {
+  SlotState& s = t->slots[slot];
+  const bool inside = level >= t->cfg.last_level && level <= t->cfg.first_level;
+  if (inside) return UWT_OK;
+  const bool do_grad = s.gradient && !s.gradient_all;
+  const bool do_cand = need_candidates && s.candidates && !s.candidates_all;
+  if (!do_grad && !do_cand) return UWT_OK;
+  ArgRegion* r;
+  int rc = acquire(t, &r);
+  if (rc) return rc;
+  if ((rc = push_slots(t, r, 1, &slot, nullptr))) return rc;
+  const LevelRange all = level_range(t->geom, 0, t->geom.levels - 1);
+  int k = 0;
+  if (do_grad) {
+    k = launch_gradient(t->geom, t->pools, 1, r->d_int, t->stream, all);
+    if (k < 0) return fail(t, UWT_E_CUDA, "gradient kernel launch failed");
+    t->launches += k;
+    s.gradient_all = true;
+  }
+  if (do_cand) {
+    k = launch_candidates(t->geom, t->pools, 1, r->d_int, t->stream, all);
+    if (k < 0) return fail(t, UWT_E_CUDA, "candidate kernel launch failed");
+    t->launches += k;
+    s.candidates_all = true;
+  }
+  return release(t, r);
+}
+
 static int check_read(uwt_tracker* t, int slot, int level) {
   if (!t) return UWT_E_INVALID;
   if (slot < 0 || slot >= t->cfg.max_frames || level < 0 || level >= t->geom.levels)
@@ -1095,6 +1139,7 @@ int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t*
   if (rc) return rc;
   if (!t->slots[slot].gradient) return fail(t, UWT_E_STATE, "slot %d has no gradients", slot);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  if ((rc = complete_levels(t, slot, level, false))) return rc;
   const LevelGeom& L = t->geom.lv[level];
   const size_t off = (size_t)slot * t->geom.plane_elems + L.plane_off;
   if (gx || gy) {
@@ -1106,7 +1151,8 @@ int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t*
     ArgRegion* r;
     if ((rc = acquire(t, &r))) { cudaFree(tmp); return rc; }
     if ((rc = push_slots(t, r, 1, &slot, nullptr))) { cudaFree(tmp); return rc; }
-    const int k = launch_gradient(t->geom, t->pools, 1, r->d_int, t->stream, tmp, tmp + pe);
+    const int k = launch_gradient(t->geom, t->pools, 1, r->d_int, t->stream,
+                                  level_range(t->geom, 0, t->geom.levels - 1), tmp, tmp + pe);
     if (k > 0) t->launches += k;
     release(t, r);
     cudaError_t e = cudaSuccess;
@@ -1134,6 +1180,7 @@ int uwt_get_candidate_count(uwt_tracker* t, int slot, int level, int* n) {
   if (!n) return fail(t, UWT_E_INVALID, "n is NULL");
   if (!t->slots[slot].candidates) return fail(t, UWT_E_STATE, "slot %d has no candidates", slot);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  if ((rc = complete_levels(t, slot, level, true))) return rc;
   uint32_t v = 0;
   UWT_CUDA(t, cudaMemcpyAsync(&v, t->pools.ncand + (size_t)slot * kMaxLevels + level, sizeof(v),
                               cudaMemcpyDeviceToHost, t->stream));

@@ -154,14 +154,14 @@ __device__ __forceinline__ void patch_img_tile_borders(uint8_t* tile, const Leve
 // 0/1 results into four packed byte counters: a (column, 64-row segment) count is at most 64.
 __global__ void __launch_bounds__(256)
 cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                  const int* __restrict__ slots, int n_slots) {
+                  const int* __restrict__ slots, int n_slots, int item_begin, int item_count) {
   __shared__ uint32_t part[8][32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int total = geom.warp_items_total * n_slots;
+  const int total = item_count * n_slots;
   constexpr int kRowsPerWarp = kSegRows / 8;
   for (int work = blockIdx.x; work < total; work += gridDim.x) {
-    const TileItem it = locate_item(geom, work % geom.warp_items_total);
-    const int slot = slots[work / geom.warp_items_total];
+    const TileItem it = locate_item(geom, work % item_count + item_begin);
+    const int slot = slots[work / item_count];
     const LevelGeom& L = geom.lv[it.lvl];
     const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
     const int ithr = pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
@@ -200,9 +200,9 @@ cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
 
 __global__ void __launch_bounds__(1024)
 cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                 const int* __restrict__ slots) {
+                 const int* __restrict__ slots, int lvl_begin) {
   __shared__ uint32_t warp_tot[32];
-  const int lvl = blockIdx.x;
+  const int lvl = blockIdx.x + lvl_begin;
   const int slot = slots[blockIdx.y];
   const LevelGeom& L = geom.lv[lvl];
   const int M = L.w * L.nseg;
@@ -242,15 +242,15 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
 
 __global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                    const int* __restrict__ slots, int n_slots) {
+                    const int* __restrict__ slots, int n_slots, int item_begin, int item_count) {
   __shared__ __align__(16) uint8_t sg[2][kSegRows * kTilePitch8];
   __shared__ __align__(16) uint8_t si[2][kImgTileRows * kImgTilePitch];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int total = geom.warp_items_total * n_slots;
+  const int total = item_count * n_slots;
   const uint32_t lt_mask = (1u << lane) - 1u;
   auto issue = [&](int work, int buf) {
-    const TileItem it = locate_item(geom, work % geom.warp_items_total);
-    const int slot = slots[work / geom.warp_items_total];
+    const TileItem it = locate_item(geom, work % item_count + item_begin);
+    const int slot = slots[work / item_count];
     const LevelGeom& L = geom.lv[it.lvl];
     const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off;
     load_tile_u8(pools.g + pbase, L, it.strip * kStripW, it.seg * kSegRows, sg[buf], t);
@@ -269,8 +269,8 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
       cp_async_wait<0>();
     }
     __syncthreads();
-    const TileItem it = locate_item(geom, work % geom.warp_items_total);
-    const int slot = slots[work / geom.warp_items_total];
+    const TileItem it = locate_item(geom, work % item_count + item_begin);
+    const int slot = slots[work / item_count];
     const LevelGeom& L = geom.lv[it.lvl];
     const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
     const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
@@ -316,10 +316,11 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
   }
 }
 
-int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st) {
+int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
+                      const LevelRange& lr) {
   // persistent grids: a multiple of the 148 SMs, as many CTAs per SM as the double-buffered
   // tiles allow; small jobs get one CTA per work item
-  const long long total = (long long)g.warp_items_total * n;
+  const long long total = (long long)lr.item_count * n;
   static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;  // same for every device of a box
   if (!sms) {
     int dev = 0;
@@ -333,11 +334,11 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   }
   const int grid_count = (int)std::min<long long>(total, (long long)sms * per_sm_count);
   const int grid_scatter = (int)std::min<long long>(total, (long long)sms * per_sm_scatter);
-  cand_count_kernel<<<grid_count, 256, 0, st>>>(g, p, d_slots, n);
+  cand_count_kernel<<<grid_count, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin, lr.item_count);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scan_kernel<<<dim3(g.levels, n), 1024, 0, st>>>(g, p, d_slots);
+  cand_scan_kernel<<<dim3(lr.lvl_count, n), 1024, 0, st>>>(g, p, d_slots, lr.lvl_begin);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scatter_kernel<<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n);
+  cand_scatter_kernel<<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin, lr.item_count);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 3;
 }

@@ -257,7 +257,7 @@ __device__ __forceinline__ RowWin row_windows(const uint8_t* srow, int sx) {
 template <bool kPlanes>
 __global__ void __launch_bounds__(256)
 gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                const int* __restrict__ slots, int16_t* __restrict__ gx_out,
+                const int* __restrict__ slots, int tile_begin, int16_t* __restrict__ gx_out,
                 int16_t* __restrict__ gy_out) {
   __shared__ __align__(128) uint8_t tile[kTileRows][kTileRowBytes];
   __shared__ __align__(8) uint64_t bar;
@@ -267,7 +267,7 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
   const int t = threadIdx.x;
   const int slot = slots[blockIdx.y];
   // locate (level, tile) from the flattened tile index
-  int lvl = 0, tidx = blockIdx.x;
+  int lvl = 0, tidx = blockIdx.x + tile_begin;
   while (lvl + 1 < geom.levels && tidx >= geom.lv[lvl + 1].tile_off) ++lvl;
   // tile_off is cumulative and increasing with the level; find the last level whose
   // tile_off <= tidx
@@ -421,12 +421,12 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
 }
 
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
-                    int16_t* gx_out, int16_t* gy_out) {
-  dim3 grid(g.grad_tiles_total, n);
+                    const LevelRange& lr, int16_t* gx_out, int16_t* gy_out) {
+  dim3 grid(lr.tile_count, n);
   if (gx_out && gy_out)
-    gradient_kernel<true><<<grid, 256, 0, st>>>(g, p, d_slots, gx_out, gy_out);
+    gradient_kernel<true><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, gx_out, gy_out);
   else
-    gradient_kernel<false><<<grid, 256, 0, st>>>(g, p, d_slots, nullptr, nullptr);
+    gradient_kernel<false><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, nullptr, nullptr);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

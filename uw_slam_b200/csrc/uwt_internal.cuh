@@ -123,6 +123,31 @@ struct RemapArgs {
   int roi_x = 0, roi_y = 0;        // top-left corner of the crop inside the maps
 };
 
+// A contiguous range of pyramid levels and the matching ranges of the flattened per-level tile
+// (K2) and work-item (K3) indices: K2 / K3 normally run on all levels; with
+// UWT_FLAG_LAZY_LEVELS only on the levels EstimatePose optimises.
+struct LevelRange {
+  int lvl_begin = 0, lvl_count = 0;
+  int tile_begin = 0, tile_count = 0;
+  int item_begin = 0, item_count = 0;
+};
+inline LevelRange level_range(const Geom& g, int lo, int hi) {
+  LevelRange r;
+  r.lvl_begin = lo;
+  r.lvl_count = hi - lo + 1;
+  for (int l = 0; l <= hi; ++l) {
+    const int tiles = g.lv[l].tiles_x * g.lv[l].tiles_y, items = g.lv[l].nstrip * g.lv[l].nseg;
+    if (l < lo) {
+      r.tile_begin += tiles;
+      r.item_begin += items;
+    } else {
+      r.tile_count += tiles;
+      r.item_count += items;
+    }
+  }
+  return r;
+}
+
 // kernel launchers (each returns the number of kernels launched, or <0 on launch error)
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
                    size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st,
@@ -130,8 +155,9 @@ int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, con
 int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, const short2* map1,
                  const uint16_t* map2, int out_w, int out_h, uint8_t* d_dst, cudaStream_t st);
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
-                    int16_t* gx_out = nullptr, int16_t* gy_out = nullptr);
-int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st);
+                    const LevelRange& lr, int16_t* gx_out = nullptr, int16_t* gy_out = nullptr);
+int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
+                      const LevelRange& lr);
 constexpr int UWT_EST_MMA = 0;        // Gram accumulator in fp64 tensor-core fragments
 constexpr int UWT_EST_REGISTERS = 1;  // 27 fp64 register accumulators per thread
 int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
