@@ -524,3 +524,38 @@ def test_lazy_levels_flag_is_observationally_identical(oracle, pairs):
     for lvl in range(5):
         assert np.array_equal(fp.candidatePoints(lvl), ref.cand[lvl])
     t.close()
+
+
+def test_dataflow_kernel_sparse_candidates(oracle):
+    """A frame whose candidates are spread thinly over all columns: the warp-level dataflow kernel
+    has to move its 32-column transform window inside a row of 32 records."""
+    import uw_slam_b200._lib as L
+    calib = "tum"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    rng = np.random.default_rng(9)
+    B = 24
+    prevs, curs = [], []
+    for s in range(B):
+        img = np.full((h, w), 100, np.uint8)
+        # isolated bright dots, about one per 3 columns and level-0 row block: strong gradients
+        # on a flat background at every pyramid level
+        ys = rng.integers(8, h - 8, 700)
+        xs = rng.integers(8, w - 8, 700)
+        for y, x in zip(ys, xs):
+            img[y - 4:y + 4, x - 4:x + 4] = 255
+        prevs.append(img)
+        curs.append(np.roll(img, (1, 2), (0, 1)))
+    t = make_tracker(calib, max_frames=2 * B, flags=L.FLAG_TRACE)
+    fp = t.AddFrames(list(range(B)), np.stack(prevs))
+    fc = t.AddFrames(list(range(B, 2 * B)), np.stack(curs))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    poses = t.EstimatePose(fp, fc)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for s in range(0, B, 5):
+        rp = oracle.FrameData(prevs[s])
+        rc = oracle.FrameData(curs[s], with_candidates=False)
+        opose, _, otrace = oracle.estimate_pose(p, rp, rc)
+        assert_trace_equal(t.get_trace(s), otrace)
+        assert np.array_equal(poses[s], opose), s
+    t.close()
