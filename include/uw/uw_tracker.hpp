@@ -186,7 +186,8 @@ class Frame {
   std::vector<int16_t> gradientX(int lvl) const;
   std::vector<int16_t> gradientY(int lvl) const;
   std::vector<uint8_t> gradient(int lvl) const;
-  std::vector<float> candidatePoints(int lvl) const;  // N x 4, rows [x y 1 1]
+  std::vector<float> candidatePoints(int lvl) const;  // N x 4, rows [x y Z 1] (Z = 1 in mono)
+  std::vector<uint16_t> depths(int lvl) const;
 
  private:
   friend class Tracker;
@@ -196,8 +197,11 @@ class Frame {
 class Tracker {
  public:
   explicit Tracker(bool depth_available) {  // include/Tracker.h:97
-    if (depth_available) throw Error(UWT_E_INVALID, "depth input is not supported");
     uwt_default_config(&cfg_);
+    // depth_available_ (src/Tracker.cpp:275): candidates need depth != 0 and carry Z = d * 0.0002;
+    // UWT_DEPTH_REFERENCE reads the depth like the reference does (at<uchar> on the 16-bit image),
+    // set config().depth_mode = UWT_DEPTH_U16 for the at<ushort> reading
+    if (depth_available) cfg_.depth_mode = UWT_DEPTH_REFERENCE;
   }
   ~Tracker() {
     if (h_) uwt_destroy(h_);
@@ -244,6 +248,12 @@ class Tracker {
     f.slot = slot;
     f.tracker_ = this;
     return f;
+  }
+  // System::AddFrame depth part (src/System.cpp:241-250): 16-bit depth frame of the same slot
+  void AddDepth(Frame* f, const uint16_t* depth, size_t row_stride_bytes = 0) {
+    const size_t rs = row_stride_bytes ? row_stride_bytes : (size_t)cfg_.width * 2;
+    Check(uwt_upload_depth_frames(h_, 1, &f->slot, depth, rs, rs * cfg_.height));
+    f->depth_available_ = true;
   }
   void ApplyGradient(Frame* f) {  // include/Tracker.h:137
     Check(uwt_apply_gradient(h_, 1, &f->slot));
@@ -299,6 +309,11 @@ inline std::vector<int16_t> Frame::gradientY(int lvl) const {
 inline std::vector<uint8_t> Frame::gradient(int lvl) const {
   std::vector<uint8_t> v((size_t)tracker_->w_[lvl] * tracker_->h__[lvl]);
   tracker_->Check(uwt_get_gradients(tracker_->h_, slot, lvl, nullptr, nullptr, v.data()));
+  return v;
+}
+inline std::vector<uint16_t> Frame::depths(int lvl) const {
+  std::vector<uint16_t> v((size_t)tracker_->w_[lvl] * tracker_->h__[lvl]);
+  tracker_->Check(uwt_get_depth(tracker_->h_, slot, lvl, v.data()));
   return v;
 }
 inline std::vector<float> Frame::candidatePoints(int lvl) const {

@@ -63,6 +63,14 @@ extern "C" {
 #define UWT_WEIGHT_HUBER 2    /* north-star option (not in the reference): w = 1 for |r| <= delta,
                                  delta/|r| beyond; sqrt(w) scales Jacobian rows and residuals    */
 
+/* Depth input: Tracker::Tracker(depth_available), the depth pyramid of
+ * System::AddFrame (src/System.cpp:241-250) and the depth branch of ObtainCandidatePoints
+ * (src/Tracker.cpp:1338-1347): candidates need depth != 0 and carry Z = depth * 0.0002. */
+#define UWT_DEPTH_NONE 0      /* mono: Z = 1 for every point (src/Tracker.cpp:1349-1355)          */
+#define UWT_DEPTH_REFERENCE 1 /* as shipped: depths_[lvl].at<uchar>(y,x) on the 16-bit image, i.e.
+                                 BYTE x of row y (low / high byte of depth pixel x/2)             */
+#define UWT_DEPTH_U16 2       /* what the code evidently means: at<ushort>(y,x)                   */
+
 /* cfg.flags */
 #define UWT_FLAG_TRACE 1u /* record a per-iteration trace (uwt_get_trace); debugging/parity */
 /* A/B switch: hold the 8x8 Gram accumulator [J | 50r]^T [J | 50r] in fp64 tensor-core (DMMA
@@ -99,6 +107,7 @@ typedef struct {
   unsigned flags;            /* UWT_FLAG_*                                               */
   int weight_mode;           /* UWT_WEIGHT_* (0 = reference)                             */
   float huber_delta;         /* UWT_WEIGHT_HUBER threshold in gray levels                */
+  int depth_mode;            /* UWT_DEPTH_* (0 = mono, the reference's default run mode)  */
 } uwt_config;
 
 typedef struct {
@@ -175,6 +184,15 @@ int uwt_calculate_roi(const uint8_t* undistorted, int w, int h, size_t stride, i
  * width x height is the cropped size.  map1 == map2 == NULL switches undistortion off. */
 int uwt_set_undistortion(uwt_tracker* t, const int16_t* map1, const uint16_t* map2, int map_w,
                          int map_h, int in_w, int in_h, int roi_x, int roi_y);
+
+/* System::AddFrame with depth_available_ (src/System.cpp:241-250): copy n 16-bit depth frames
+ * (host or device memory, rows row_stride BYTES apart) into slots[i] and build their pyramids (cv::resize of
+ * CV_16U by 0.5 = 2x2 mean, ties to even).  Needs cfg.depth_mode != 0; call it after
+ * uwt_upload_frames for the same slots and before uwt_select_candidates. */
+int uwt_upload_depth_frames(uwt_tracker* t, int n, const int* slots, const uint16_t* host,
+                            size_t row_stride, size_t frame_stride);
+/* depths_[level] of a slot, dense row-major host buffer. */
+int uwt_get_depth(uwt_tracker* t, int slot, int level, uint16_t* host);
 
 /* Tracker::ApplyGradient for n slots: gradient_ (u8) on every pyramid level.  The int16
  * gradientX_ / gradientY_ values reach the tracker through the packed candidate records; the

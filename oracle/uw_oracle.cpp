@@ -396,6 +396,51 @@ int uwo_candidates(const uint8_t* g, int w, int h, double gradient_threshold, fl
   return n;
 }
 
+void uwo_depth_pyr_down(const uint16_t* src, int w, int h, uint16_t* dst) {
+  // resizeAreaFast for 16U: float sum * 0.25 -> saturate_cast<ushort>(cvRound(.)): the sum of
+  // four 16-bit values and its quarter are exact in float/double, so this is s/4 ties-to-even
+  const int w2 = w / 2, h2 = h / 2;
+  for (int y = 0; y < h2; ++y) {
+    const uint16_t* r0 = src + (size_t)(2 * y) * w;
+    const uint16_t* r1 = r0 + w;
+    for (int x = 0; x < w2; ++x) {
+      const unsigned s = (unsigned)r0[2 * x] + r0[2 * x + 1] + r1[2 * x] + r1[2 * x + 1];
+      unsigned q = s >> 2;
+      const unsigned rem = s & 3u;
+      if (rem == 3u || (rem == 2u && (q & 1u))) ++q;
+      dst[(size_t)y * w2 + x] = (uint16_t)q;
+    }
+  }
+}
+
+int uwo_candidates_depth(const uint8_t* g, const uint16_t* depth, int w, int h,
+                         double gradient_threshold, int depth_mode, float* pts4, uint16_t* zsrc) {
+  const float factor = 0.0002;  // Tracker.cpp:1316 "Factor of TUM depth images"
+  unsigned long long S = 0;
+  const long long N = (long long)w * h;
+  for (long long i = 0; i < N; ++i) S += g[i];
+  const double mean = (double)S / (double)N;               // U6
+  const float thres = (float)(mean + gradient_threshold);  // Tracker.cpp:1327
+  const int ithr = (int)std::floor(thres);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(depth);  // at<uchar> on a CV_16U Mat
+  int n = 0;
+  for (int x = 0; x < w; ++x)    // Tracker.cpp:1334
+    for (int y = 0; y < h; ++y) {  // Tracker.cpp:1335
+      // Tracker.cpp:1339,1344: at<uchar>(y,x) = data[y * step + x], step = 2 * w bytes
+      const int d = depth_mode == UWO_DEPTH_REFERENCE ? (int)bytes[(size_t)y * 2 * w + x]
+                                                      : (int)depth[(size_t)y * w + x];
+      if (d != 0 && (int)g[(size_t)y * w + x] > ithr) {
+        pts4[(size_t)n * 4 + 0] = (float)x;
+        pts4[(size_t)n * 4 + 1] = (float)y;
+        pts4[(size_t)n * 4 + 2] = d * factor;  // Tracker.cpp:1344
+        pts4[(size_t)n * 4 + 3] = 1.0f;
+        if (zsrc) zsrc[n] = (uint16_t)d;
+        ++n;
+      }
+    }
+  return n;
+}
+
 void uwo_init_pyramid(int w, int h, float fx, float fy, float cx, float cy, int levels, int* wl,
                       int* hl, float* fxl, float* fyl, float* cxl, float* cyl, float* invfxl,
                       float* invfyl) {

@@ -87,6 +87,20 @@ void uwo_gradmag(const int16_t* gx, const int16_t* gy, long long n, uint8_t* g);
  * hold w*h*4 floats.  Returns the number of candidates; rows are [x,y,1,1], x-major. */
 int uwo_candidates(const uint8_t* g, int w, int h, double gradient_threshold,
                    float* pts4, double* mean_out, int* ithr_out);
+/* ---- depth input ----
+ * System::AddFrame depth pyramid (System.cpp:248-250): cv::resize(0.5, 0.5) of a CV_16U image =
+ * 2x2 area mean rounded half-to-even (cvRound of sum * 0.25). */
+void uwo_depth_pyr_down(const uint16_t* src, int w, int h, uint16_t* dst);
+/* depth_mode of the candidate selection (Tracker.cpp:1338-1347): */
+#define UWO_DEPTH_NONE 0      /* mono: Z = depth_initialization = 1 (Tracker.cpp:1349-1355)      */
+#define UWO_DEPTH_REFERENCE 1 /* as shipped: depths_[lvl].at<uchar>(y,x), i.e. BYTE x of row y of
+                                 the 16-bit image (low/high byte of pixel x/2), Z = byte * 0.0002  */
+#define UWO_DEPTH_U16 2       /* what the code evidently means: at<ushort>(y,x), Z = d * 0.0002   */
+/* Tracker::ObtainCandidatePoints with depth_available_ (Tracker.cpp:1338-1347): rows [x,y,Z,1]
+ * for pixels with filtered != 0 AND depth != 0.  zsrc (optional) receives the integer depth used. */
+int uwo_candidates_depth(const uint8_t* g, const uint16_t* depth, int w, int h,
+                         double gradient_threshold, int depth_mode, float* pts4, uint16_t* zsrc);
+
 /* Tracker::InitializePyramid, Tracker.cpp:297-340. Arrays of length `levels`. */
 void uwo_init_pyramid(int w, int h, float fx, float fy, float cx, float cy, int levels,
                       int* wl, int* hl, float* fxl, float* fyl, float* cxl, float* cyl,

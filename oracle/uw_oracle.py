@@ -15,6 +15,7 @@ MAX_LEVELS = 8
 SOLVE_LU, SOLVE_INVERSE = 0, 1
 ACCUM_DOUBLE, ACCUM_LONGDOUBLE = 0, 1
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
+DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16 = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -309,17 +310,53 @@ def lu_invert6(A):
     return Ai, ok
 
 
+def depth_pyr_down(d):
+    h, w = d.shape
+    d = np.ascontiguousarray(d, np.uint16)
+    out = np.empty((h // 2, w // 2), np.uint16)
+    f = lib().uwo_depth_pyr_down
+    f.argtypes = [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(C.c_uint16)]
+    f.restype = None
+    f(_p(d, C.c_uint16), w, h, _p(out, C.c_uint16))
+    return out
+
+
+def candidates_depth(g, depth, gradient_threshold=20.0, depth_mode=DEPTH_REFERENCE):
+    """Depth branch of ObtainCandidatePoints: (N x 4 points [x, y, Z, 1], integer depths used)."""
+    h, w = g.shape
+    g = np.ascontiguousarray(g, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    pts = np.empty((h * w, 4), np.float32)
+    z = np.empty(h * w, np.uint16)
+    f = lib().uwo_candidates_depth
+    f.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_double,
+                  C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint16)]
+    f.restype = C.c_int
+    n = f(_p(g, C.c_uint8), _p(depth, C.c_uint16), w, h, gradient_threshold, depth_mode,
+          _p(pts, C.c_float), _p(z, C.c_uint16))
+    return pts[:n].copy(), z[:n].copy()
+
+
 class FrameData:
     """What uw::Frame holds after pyramid + ApplyGradient + ObtainCandidatePoints."""
 
-    def __init__(self, img, levels=5, gradient_threshold=20.0, with_candidates=True):
+    def __init__(self, img, levels=5, gradient_threshold=20.0, with_candidates=True, depth=None,
+                 depth_mode=DEPTH_NONE):
         self.images = build_pyramid(img, levels)
         self.gx, self.gy, self.g, self.cand, self.mean, self.ithr = [], [], [], [], [], []
+        self.depths, self.zsrc = [], []
+        if depth is not None and depth_mode != DEPTH_NONE:
+            self.depths = [np.ascontiguousarray(depth, np.uint16)]
+            for _ in range(1, levels):
+                self.depths.append(depth_pyr_down(self.depths[-1]))
         if with_candidates:
-            for im in self.images:
+            for lvl, im in enumerate(self.images):
                 gx, gy = scharr(im)
                 g = gradmag(gx, gy)
                 c, m, t = candidates(g, gradient_threshold)
+                if self.depths:
+                    c, z = candidates_depth(g, self.depths[lvl], gradient_threshold, depth_mode)
+                    self.zsrc.append(z)
                 self.gx.append(gx)
                 self.gy.append(gy)
                 self.g.append(g)

@@ -1,0 +1,103 @@
+"""Depth input: Tracker(depth_available=true), the 16-bit depth pyramid of
+System::AddFrame (System.cpp:241-250) and the depth branch of ObtainCandidatePoints
+(Tracker.cpp:1338-1347), in both readings of `depths_[lvl].at<uchar>(y,x)`; GPU vs oracle."""
+import numpy as np
+import pytest
+
+from uw_slam_b200 import synth
+
+
+def make_depth(shape, seed, holes=True):
+    """A smooth 16-bit depth map around 1.5-4 m (TUM factor 5000/m ~ here 1/0.0002), with holes
+    (depth 0 = no measurement) and values whose low byte is 0 (matters to the at<uchar> read)."""
+    rng = np.random.default_rng(seed)
+    h, w = shape
+    ys, xs = np.mgrid[0:h, 0:w]
+    d = 9000 + 4000 * np.sin(xs * 0.013 + seed) * np.cos(ys * 0.017) + rng.integers(0, 40, shape)
+    d = d.astype(np.uint16)
+    if holes:
+        d[rng.random(shape) < 0.07] = 0
+        d[h // 3:h // 3 + 9, w // 4:w // 2] = 0
+        d[5::17, 3::11] &= 0xFF00
+    return d
+
+
+def test_depth_pyramid_matches_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    d = make_depth((480, 640), 1)
+    for _ in range(4):
+        nxt = oracle.depth_pyr_down(d)
+        assert np.array_equal(nxt, cv2.resize(d, None, fx=0.5, fy=0.5))   # System.cpp:249
+        d = nxt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("calib,seed,batch", [("small", 3, 1), ("tum", 1, 1), ("euroc", 2, 1),
+                                              ("small", 10, 30)])
+def test_depth_tracking_matches_oracle(oracle, calib, seed, batch, mode):
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    pairs = [synth.render_pair(calib, seed + i)[:2] for i in range(batch)]
+    deps = [make_depth((h, w), seed + i) for i in range(batch)]
+    t = U.Tracker(True, depth_mode=mode)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=2 * batch, flags=L.FLAG_TRACE)
+    fp = t.AddFrames(list(range(batch)), np.stack([p[0] for p in pairs]))
+    fc = t.AddFrames(list(range(batch, 2 * batch)), np.stack([p[1] for p in pairs]))
+    t.ApplyGradient(fp)
+    with pytest.raises(U.UwtError):      # the candidate rule needs the depth frame
+        t.ObtainCandidatePoints(fp)
+    t.AddDepthFrames([f.slot for f in fp], np.stack(deps))
+    t.ObtainCandidatePoints(fp)
+    poses, stats = t.EstimatePose(fp, fc, return_stats=True)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for i in range(batch):
+        rp = oracle.FrameData(pairs[i][0], depth=deps[i], depth_mode=mode)
+        rc = oracle.FrameData(pairs[i][1], with_candidates=False)
+        if i == 0:
+            for lvl in range(5):
+                assert np.array_equal(fp[0].depth(lvl), rp.depths[lvl]), lvl
+                c = fp[0].candidatePoints(lvl)
+                assert c.shape == rp.cand[lvl].shape, (lvl, c.shape, rp.cand[lvl].shape)
+                assert np.array_equal(c, rp.cand[lvl]), lvl      # rows [x, y, Z, 1]
+            assert 0 < rp.cand[1].shape[0] < oracle.FrameData(pairs[i][0]).cand[1].shape[0]
+        opose, ostats, otrace = oracle.estimate_pose(p, rp, rc)
+        tr = t.get_trace(i)
+        assert [(a.level, a.k, a.n_valid, a.broke, a.sum_r2) for a in tr] == \
+            [(b.level, b.k, b.n_valid, b.broke, b.sum_r2) for b in otrace], i
+        for a, b in zip(tr, otrace):
+            assert np.array_equal(np.array(a.A[:]), np.array(b.A[:])), (i, b.level, b.k)
+            assert np.array_equal(np.array(a.delta[:]), np.array(b.delta[:])), (i, b.level, b.k)
+            assert np.array_equal(np.array(a.pose[:]), np.array(b.pose[:])), (i, b.level, b.k)
+        assert np.array_equal(poses[i], opose), i
+    t.close()
+
+
+@pytest.mark.gpu
+def test_depth_api_rules():
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    w, h, fx, fy, cx, cy = synth.CALIB["small"]
+    K = U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK()
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, K)
+    with pytest.raises(U.UwtError):      # mono tracker takes no depth
+        t.AddDepthFrames([0], np.ones((h, w), np.uint16))
+    t.close()
+    for bad in (dict(depth_mode=3), dict(depth_mode=1, weight_mode=1),
+                dict(depth_mode=2, flags=L.FLAG_DMMA_ACCUM)):
+        with pytest.raises(U.UwtError):
+            U.Tracker(False).InitializePyramid(w, h, K, **bad)
+    # all-zero depth: no candidates anywhere, identity pose (ARITHMETIC.md U2)
+    t = U.Tracker(True)
+    t.InitializePyramid(w, h, K)
+    prev, cur = synth.render_pair("small", 0)[:2]
+    fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.AddDepthFrames([0], np.zeros((h, w), np.uint16))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    assert all(fp.candidatePoints(l).shape[0] == 0 for l in range(5))
+    assert np.allclose(t.EstimatePose(fp, fc)[0], [0, 0, 0, 1, 0, 0, 0])
+    t.close()

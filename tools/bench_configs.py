@@ -11,6 +11,7 @@
 Launch like bench.py (python tools/bench_configs.py ... or torchrun for N > 1).  One JSON line.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -106,7 +107,15 @@ def batch8192(args, torch, dist, rank, local_rank, world):
     mine = hi - lo
     chunk = min(args.chunk, mine)
     t = make_tracker(calib, local_rank, max_frames=2 * chunk, flags=args.flags,
-                     weight_mode=args.weights)
+                     weight_mode=args.weights, depth_mode=args.depth)
+    depth = None
+    if args.depth:
+        # one smooth synthetic depth map with holes, shared by all pairs (resident in HBM)
+        ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev),
+                                indexing="ij")
+        dm = (9000 + 4000 * torch.sin(xs * 0.013) * torch.cos(ys * 0.017)).to(torch.int32)
+        dm[(xs * 7 + ys * 13) % 17 == 0] = 0
+        depth = dm.to(torch.uint16).contiguous()
     # resident inputs: all of this rank's pairs, rendered on the device
     prev = torch.empty((mine, h, w), dtype=torch.uint8, device=dev)
     cur = torch.empty_like(prev)
@@ -122,6 +131,10 @@ def batch8192(args, torch, dist, rank, local_rank, world):
             n = min(chunk, mine - a)
             t.AddFramesDevice(ps[:n], prev[a].data_ptr())
             t.AddFramesDevice(cs[:n], cur[a].data_ptr())
+            if depth is not None:
+                # frame_stride 0: every slot gets the same (device-resident) depth frame
+                t._check(t._lib.uwt_upload_depth_frames(t._h, n, (C.c_int * n)(*ps[:n]),
+                                                        depth.data_ptr(), w * 2, 0))
             t.ApplyGradient(ps[:n])
             t.ObtainCandidatePoints(ps[:n])
             out[a:a + n] = t.EstimatePose(ps[:n], cs[:n])
@@ -140,15 +153,17 @@ def batch8192(args, torch, dist, rank, local_rank, world):
                      "candidates, estimate per pair; inputs resident in HBM)",
            "value": total / float(dt.item()), "unit": "tracks/s", "pairs": total,
            "n_gpus": world, "scaling": "strong", "chunk": chunk, "flags": args.flags,
-           "weights": ["identity", "tukey_mad", "huber"][args.weights]}
+           "weights": ["identity", "tukey_mad", "huber"][args.weights], "depth_mode": args.depth}
     if rank == 0:
         # spot-check 4 pairs against the oracle
         from oracle import uw_oracle as O
         p = O.default_params(*synth.CALIB[calib], weight_mode=args.weights)
         same = True
+        dnp = depth.cpu().numpy() if depth is not None else None
         for i in [0, 1, mine // 2, mine - 1]:
             a, b = prev[i].cpu().numpy(), cur[i].cpu().numpy()
-            op, _, _ = O.estimate_pose(p, O.FrameData(a), O.FrameData(b, with_candidates=False))
+            op, _, _ = O.estimate_pose(p, O.FrameData(a, depth=dnp, depth_mode=args.depth),
+                                       O.FrameData(b, with_candidates=False))
             same &= bool(np.array_equal(op, out[i]))
         res["spot_check_bit_identical_to_oracle"] = same
     return res
@@ -218,6 +233,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="uwt_config.flags (4 = cluster kernel)")
     ap.add_argument("--weights", type=int, default=0, help="0 identity, 1 Tukey/MAD, 2 Huber")
+    ap.add_argument("--depth", type=int, default=0,
+                    help="depth input: 0 mono, 1 reference (at<uchar>), 2 at<ushort>")
     args = ap.parse_args()
     sys.stdout.flush()
     real_stdout = os.fdopen(os.dup(1), "w")   # banners (NCCL ...) go to stderr, the JSON here

@@ -16,6 +16,7 @@ FLAG_DMMA_ACCUM = 2
 FLAG_CLUSTER_KERNEL = 4
 FLAG_LAZY_LEVELS = 8
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
+DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16 = 0, 1, 2
 KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 
 
@@ -27,7 +28,7 @@ class Config(C.Structure):
         ("max_iterations", C.c_int), ("epsilon", C.c_float), ("residual_scale", C.c_float),
         ("gradient_threshold", C.c_double), ("solve_mode", C.c_int), ("device", C.c_int),
         ("max_frames", C.c_int), ("cluster_size", C.c_int), ("flags", C.c_uint),
-        ("weight_mode", C.c_int), ("huber_delta", C.c_float),
+        ("weight_mode", C.c_int), ("huber_delta", C.c_float), ("depth_mode", C.c_int),
     ]
 
 
@@ -76,6 +77,8 @@ SIGNATURES = {
     "uwt_calculate_roi": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_size_t, _ip]),
     "uwt_set_undistortion": (C.c_int, [_H, _i16p, C.POINTER(C.c_uint16), C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int]),
+    "uwt_upload_depth_frames": (C.c_int, [_H, C.c_int, _ip, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "uwt_get_depth": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_uint16)]),
     "uwt_apply_gradient": (C.c_int, [_H, C.c_int, _ip]),
     "uwt_select_candidates": (C.c_int, [_H, C.c_int, _ip]),
     "uwt_estimate_pose": (C.c_int, [_H, C.c_int, _ip, _ip, _fp, _fp, C.POINTER(TrackStats)]),

@@ -32,7 +32,7 @@ constexpr int kTraceProblems = 64;
 thread_local std::string g_create_error;
 
 struct SlotState {
-  bool pyramid = false, gradient = false, candidates = false;
+  bool pyramid = false, gradient = false, candidates = false, depth = false;
   // UWT_FLAG_LAZY_LEVELS: gradient / candidates exist on the optimised levels only until a
   // read-back asks for another level (then all levels are materialised)
   bool gradient_all = false, candidates_all = false;
@@ -175,6 +175,7 @@ int build_geom(const uwt_config& c, Geom& g) {
   g.solve_mode = c.solve_mode;
   g.weight_mode = c.weight_mode;
   g.huber_delta = c.huber_delta;
+  g.depth_mode = c.depth_mode;
   size_t plane = 0, cand = 0, rec = 0, cnt = 0;
   int tiles = 0, items = 0;
   // Tracker::InitializePyramid, Tracker.cpp:297-340 (same expression types as the source:
@@ -269,7 +270,7 @@ void destroy_impl(uwt_tracker* t) {
   Pools& p = t->pools;
   cudaFree(p.img); cudaFree(p.g); cudaFree(p.gpart);
   cudaFree(p.ticket); cudaFree(p.ithr); cudaFree(p.cnt); cudaFree(p.ncand);
-  cudaFree(p.cand_xy); cudaFree(p.rec);
+  cudaFree(p.cand_xy); cudaFree(p.rec); cudaFree(p.dep); cudaFree(p.recz);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   for (ArgRegion& r : t->ring) {
     if (r.h_int) cudaFreeHost(r.h_int);
@@ -336,6 +337,7 @@ int uwt_default_config(uwt_config* cfg) {
   cfg->flags = 0;
   cfg->weight_mode = UWT_WEIGHT_IDENTITY;  // Tracker.cpp:495
   cfg->huber_delta = 10.0f;
+  cfg->depth_mode = UWT_DEPTH_NONE;  // Tracker(depth_available = false), System.cpp:121
   return UWT_OK;
 }
 
@@ -368,6 +370,12 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
     return fail(nullptr, UWT_E_INVALID, "bad weight_mode %d", c.weight_mode);
   if (c.weight_mode == UWT_WEIGHT_HUBER && !(c.huber_delta > 0.0f))
     return fail(nullptr, UWT_E_INVALID, "huber_delta must be > 0");
+  if (c.depth_mode < UWT_DEPTH_NONE || c.depth_mode > UWT_DEPTH_U16)
+    return fail(nullptr, UWT_E_INVALID, "bad depth_mode %d", c.depth_mode);
+  if (c.depth_mode != UWT_DEPTH_NONE &&
+      (c.weight_mode != UWT_WEIGHT_IDENTITY || (c.flags & UWT_FLAG_DMMA_ACCUM)))
+    return fail(nullptr, UWT_E_INVALID,
+                "depth input supports identity weights and the register accumulator only");
   if (c.weight_mode != UWT_WEIGHT_IDENTITY && (c.flags & UWT_FLAG_DMMA_ACCUM))
     return fail(nullptr, UWT_E_INVALID, "UWT_FLAG_DMMA_ACCUM supports identity weights only");
   if (c.cluster_size != 0 && c.cluster_size != 1 && c.cluster_size != 2 && c.cluster_size != 4 &&
@@ -411,6 +419,11 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   CREATE_CUDA(cudaMalloc(&p.ncand, F * kMaxLevels * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.cand_xy, F * g.cand_elems * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.rec, F * g.rec_elems * sizeof(uint64_t)));
+  if (c.depth_mode != UWT_DEPTH_NONE) {
+    CREATE_CUDA(cudaMalloc(&p.dep, F * g.plane_elems * sizeof(uint16_t)));
+    CREATE_CUDA(cudaMalloc(&p.recz, F * g.rec_elems * sizeof(uint16_t)));
+    CREATE_CUDA(cudaMemsetAsync(p.dep, 0, F * g.plane_elems * sizeof(uint16_t), t->stream));
+  }
   CREATE_CUDA(cudaMemsetAsync(p.ticket, 0, F * kMaxLevels * sizeof(uint32_t), t->stream));
   CREATE_CUDA(cudaMemsetAsync(p.ncand, 0, F * kMaxLevels * sizeof(uint32_t), t->stream));
   // pitch padding bytes are read (never used) by vector loads: keep them defined
@@ -555,7 +568,7 @@ static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t
   for (int i = 0; i < n; ++i) {
     SlotState& s = t->slots[slots[i]];
     s.pyramid = true;
-    s.gradient = s.candidates = s.gradient_all = s.candidates_all = false;
+    s.gradient = s.candidates = s.gradient_all = s.candidates_all = s.depth = false;
   }
   return UWT_OK;
 }
@@ -611,6 +624,57 @@ int uwt_set_frames_device(uwt_tracker* t, int n, const int* slots, const uint8_t
     return fail(t, UWT_E_INVALID, "dev NULL or row_stride < source width");
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   return pyramid_common(t, n, slots, dev, row_stride, frame_stride);
+}
+
+int uwt_upload_depth_frames(uwt_tracker* t, int n, const int* slots, const uint16_t* host,
+                            size_t row_stride, size_t frame_stride) {
+  int rc = check_slots(t, n, slots);
+  if (rc) return rc;
+  if (t->cfg.depth_mode == UWT_DEPTH_NONE)
+    return fail(t, UWT_E_STATE, "the tracker was created without depth input (cfg.depth_mode)");
+  const size_t w = t->cfg.width, h = t->cfg.height;
+  if (!host || row_stride < w * sizeof(uint16_t))
+    return fail(t, UWT_E_INVALID, "host NULL or row_stride < 2 * width bytes");
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  const LevelGeom& L0 = t->geom.lv[0];
+  for (int i = 0; i < n; ++i) {
+    uint16_t* dst = t->pools.dep + (size_t)slots[i] * t->geom.plane_elems + L0.plane_off;
+    UWT_CUDA(t, cudaMemcpy2DAsync(dst, (size_t)L0.pitch * sizeof(uint16_t),
+                                  reinterpret_cast<const uint8_t*>(host) + (size_t)i * frame_stride,
+                                  row_stride, w * sizeof(uint16_t), h, cudaMemcpyDefault,
+                                  t->stream));  // host or device-resident depth frames (UVA)
+  }
+  ArgRegion* r;
+  if ((rc = acquire(t, &r))) return rc;
+  if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
+  ProfSpan span(t, UWT_K_PYRAMID);
+  const int k = launch_depth_pyramid(t->geom, t->pools, n, r->d_int, t->stream);
+  span.done(k);
+  if (k < 0) return fail(t, UWT_E_CUDA, "depth pyramid kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  if ((rc = release(t, r))) return rc;
+  for (int i = 0; i < n; ++i) {
+    SlotState& s = t->slots[slots[i]];
+    s.depth = true;
+    s.candidates = s.candidates_all = false;  // the candidate rule depends on the depth
+  }
+  return UWT_OK;
+}
+
+int uwt_get_depth(uwt_tracker* t, int slot, int level, uint16_t* host) {
+  if (!t) return UWT_E_INVALID;
+  if (slot < 0 || slot >= t->cfg.max_frames || level < 0 || level >= t->geom.levels || !host)
+    return fail(t, UWT_E_INVALID, "slot %d / level %d out of range or host NULL", slot, level);
+  if (!t->slots[slot].depth) return fail(t, UWT_E_STATE, "slot %d has no depth frame", slot);
+  UWT_CUDA(t, cudaSetDevice(t->cfg.device));
+  const LevelGeom& L = t->geom.lv[level];
+  UWT_CUDA(t, cudaMemcpy2DAsync(host, (size_t)L.w * 2,
+                                t->pools.dep + (size_t)slot * t->geom.plane_elems + L.plane_off,
+                                (size_t)L.pitch * 2, (size_t)L.w * 2, L.h, cudaMemcpyDeviceToHost,
+                                t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+  return UWT_OK;
 }
 
 int uwt_set_undistortion(uwt_tracker* t, const int16_t* map1, const uint16_t* map2, int map_w,
@@ -695,6 +759,10 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
   for (int i = 0; i < n; ++i)
     if (!t->slots[slots[i]].gradient)
       return fail(t, UWT_E_STATE, "slot %d has no gradients (call uwt_apply_gradient)", slots[i]);
+  for (int i = 0; i < n; ++i)
+    if (t->cfg.depth_mode != UWT_DEPTH_NONE && !t->slots[slots[i]].depth)
+      return fail(t, UWT_E_STATE, "slot %d has no depth frame (call uwt_upload_depth_frames)",
+                  slots[i]);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   ArgRegion* r;
   if ((rc = acquire(t, &r))) return rc;
@@ -747,7 +815,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   {
     const LevelGeom& Lf = t->geom.lv[t->cfg.last_level];
     if (n == 1 && t->cfg.cluster_size == 0 && !(t->cfg.flags & UWT_FLAG_TRACE) &&
-        t->cfg.weight_mode == UWT_WEIGHT_IDENTITY &&
+        t->cfg.weight_mode == UWT_WEIGHT_IDENTITY && t->cfg.depth_mode == UWT_DEPTH_NONE &&
         (long long)Lf.w * Lf.h >= (1 << 20)) {
       ShardState s;
       std::memset(&s, 0, sizeof(s));
@@ -816,6 +884,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   const bool use_flow = n >= kFlowMinProblems && n < kFlowMaxProblems &&
                         t->cfg.cluster_size == 0 &&
                         t->cfg.weight_mode == UWT_WEIGHT_IDENTITY &&
+                        t->cfg.depth_mode == UWT_DEPTH_NONE &&
                         !(t->cfg.flags & (UWT_FLAG_DMMA_ACCUM | UWT_FLAG_CLUSTER_KERNEL));
   if (use_flow) {
     const size_t need = flow_workspace_bytes(t->geom, n);
@@ -885,8 +954,8 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
   if ((rc = check_slots(t, 1, &cur_slot))) return rc;
   if (nranks < 1 || rank < 0 || rank >= nranks)
     return fail(t, UWT_E_INVALID, "bad shard rank %d of %d", rank, nranks);
-  if (t->cfg.weight_mode != UWT_WEIGHT_IDENTITY)
-    return fail(t, UWT_E_INVALID, "the sharded mode supports identity weights only");
+  if (t->cfg.weight_mode != UWT_WEIGHT_IDENTITY || t->cfg.depth_mode != UWT_DEPTH_NONE)
+    return fail(t, UWT_E_INVALID, "the sharded mode supports identity weights, mono input only");
   if (!t->slots[prev_slot].candidates)
     return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slot);
   if (!t->slots[cur_slot].pyramid) return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slot);
@@ -1200,6 +1269,25 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
     return fail(t, UWT_E_INVALID, "capacity %d < %d candidates", capacity_rows, cnt);
   if (cnt == 0) return UWT_OK;
   const LevelGeom& L = t->geom.lv[level];
+  // depth modes: Z = depth * factor (Tracker.cpp:1344) from the level's depth plane
+  std::vector<uint16_t> dplane;
+  if (t->cfg.depth_mode != UWT_DEPTH_NONE) {
+    dplane.resize((size_t)L.w * L.h);
+    rc = uwt_get_depth(t, slot, level, dplane.data());
+    if (rc) return rc;
+  }
+  const float factor = 0.0002;  // Tracker.cpp:1316
+  auto z_of = [&](int x, int y) -> float {
+    if (dplane.empty()) return 1.0f;  // depth_initialization, Tracker.cpp:1317
+    int d;
+    if (t->cfg.depth_mode == UWT_DEPTH_REFERENCE) {
+      const unsigned v = dplane[(size_t)y * L.w + (x >> 1)];
+      d = (x & 1) ? (int)(v >> 8) : (int)(v & 0xFFu);
+    } else {
+      d = dplane[(size_t)y * L.w + x];
+    }
+    return d * factor;
+  };
   if (L.rec_off >= 0) {
     // optimised levels keep only the packed records; (x, y) are their low 24 bits
     std::vector<uint64_t> rec(cnt);
@@ -1210,7 +1298,7 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
     for (int i = 0; i < cnt; ++i) {  // candidatePoints_ rows, Tracker.cpp:1351-1355
       pts4[i * 4 + 0] = (float)(rec[i] & 0xFFFu);
       pts4[i * 4 + 1] = (float)((rec[i] >> 12) & 0xFFFu);
-      pts4[i * 4 + 2] = 1.0f;
+      pts4[i * 4 + 2] = z_of((int)(rec[i] & 0xFFFu), (int)((rec[i] >> 12) & 0xFFFu));
       pts4[i * 4 + 3] = 1.0f;
     }
     return UWT_OK;
@@ -1223,7 +1311,7 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
   for (int i = 0; i < cnt; ++i) {  // candidatePoints_ rows, Tracker.cpp:1351-1355
     pts4[i * 4 + 0] = (float)(xy[i] & 0xFFFFu);
     pts4[i * 4 + 1] = (float)(xy[i] >> 16);
-    pts4[i * 4 + 2] = 1.0f;
+    pts4[i * 4 + 2] = z_of((int)(xy[i] & 0xFFFFu), (int)(xy[i] >> 16));
     pts4[i * 4 + 3] = 1.0f;
   }
   return UWT_OK;

@@ -178,8 +178,25 @@ cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
         w[r] = (gy < L.h) ? __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx))
                           : 0u;
       }
+      if (geom.depth_mode == UWT_DEPTH_NONE) {
 #pragma unroll
-      for (int r = 0; r < kRowsPerWarp; ++r) acc += __vsetgtu4(w[r], thr4);
+        for (int r = 0; r < kRowsPerWarp; ++r) acc += __vsetgtu4(w[r], thr4);
+      } else {
+        // depth branch (Tracker.cpp:1339): a pixel counts only if its depth is non-zero too
+        const uint16_t* dplane = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off;
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+          const int gy = y0 + wid * kRowsPerWarp + r;
+          uint32_t nz = 0;
+          if (gy < L.h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (gx + i < L.w && depth_at(dplane, L.pitch, gx + i, gy, geom.depth_mode) != 0)
+                nz |= 1u << (8 * i);
+          }
+          acc += __vsetgtu4(w[r], thr4) & nz;
+        }
+      }
     }
     part[wid][lane] = acc;
     __syncthreads();
@@ -281,6 +298,9 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
     const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
     uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
     uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
+    const bool use_depth = geom.depth_mode != UWT_DEPTH_NONE;
+    const uint16_t* dplane = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off;
+    uint16_t* recz = pools.recz + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
     // start offsets of this warp's 16 (column, segment) runs: one per lane
     uint32_t my_base = 0;
     {
@@ -295,10 +315,16 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
 #pragma unroll
       for (int ch = 0; ch < kSegRows / 32; ++ch) {
         const int row = ch * 32 + lane, y = y0 + row;
-        const bool sel = (y < L.h) && ((uint32_t)tg[row * kTilePitch8 + c] > ithr);
+        bool sel = (y < L.h) && ((uint32_t)tg[row * kTilePitch8 + c] > ithr);
+        int dz = 0;
+        if (use_depth && sel) {  // Tracker.cpp:1339: depth != 0 as well
+          dz = depth_at(dplane, L.pitch, x, y, geom.depth_mode);
+          sel = dz != 0;
+        }
         const uint32_t b = __ballot_sync(0xffffffffu, sel);
         if (sel) {
           const uint32_t o = base + __popc(b & lt_mask);
+          if (has_rec && use_depth) recz[o] = (uint16_t)dz;
           if (has_rec) {
             // a record carries (x, y) itself: the plain (x, y) list is kept only for the levels
             // EstimatePose never optimises (read-back of candidatePoints_ decodes either form)

@@ -166,6 +166,48 @@ int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, con
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// Depth pyramid (System.cpp:248-250): cv::resize(depths_[l-1], depths_[l], Size(), 0.5, 0.5) on
+// CV_16U = mean of the 2x2 block rounded half-to-even.  One launch per level; a thread makes two
+// horizontally adjacent outputs from two 8-byte loads.
+__global__ void __launch_bounds__(256)
+depth_down_kernel(const __grid_constant__ Geom geom, const Pools pools,
+                  const int* __restrict__ slots, int lvl) {
+  const LevelGeom& S = geom.lv[lvl - 1];
+  const LevelGeom& D = geom.lv[lvl];
+  const int slot = slots[blockIdx.z];
+  const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 2, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= D.w || y >= D.h) return;
+  const uint16_t* src = pools.dep + (size_t)slot * geom.plane_elems + S.plane_off;
+  uint16_t* dst = pools.dep + (size_t)slot * geom.plane_elems + D.plane_off;
+  // pitch is a multiple of 16 elements and x is even: 8-byte aligned loads of 4 source pixels
+  const ushort4 a = *reinterpret_cast<const ushort4*>(src + (size_t)(2 * y) * S.pitch + 2 * x);
+  const ushort4 b = *reinterpret_cast<const ushort4*>(src + (size_t)(2 * y + 1) * S.pitch + 2 * x);
+  auto mean4 = [](unsigned s) {
+    unsigned q = s >> 2;
+    const unsigned rem = s & 3u;
+    return q + ((rem == 3u || (rem == 2u && (q & 1u))) ? 1u : 0u);
+  };
+  const unsigned o0 = mean4((unsigned)a.x + a.y + b.x + b.y);
+  const unsigned o1 = mean4((unsigned)a.z + a.w + b.z + b.w);
+  uint16_t* o = dst + (size_t)y * D.pitch + x;
+  if (x + 1 < D.w)
+    *reinterpret_cast<uint32_t*>(o) = o0 | (o1 << 16);
+  else
+    *o = (uint16_t)o0;
+}
+
+int launch_depth_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots,
+                         cudaStream_t st) {
+  int k = 0;
+  for (int l = 1; l < g.levels; ++l) {
+    dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 3) / 4, n);
+    depth_down_kernel<<<grid, 256, 0, st>>>(g, p, d_slots, l);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    ++k;
+  }
+  return k;
+}
+
 // CameraModel::Undistort (CameraModel.cpp:101-103): plain remap of one image, no pyramid.
 __global__ void __launch_bounds__(256)
 remap_kernel(const uint8_t* __restrict__ src, size_t row_stride, int in_w, int in_h,

@@ -54,6 +54,7 @@ struct Geom {
   int solve_mode;
   int weight_mode;    // UWT_WEIGHT_*
   float huber_delta;
+  int depth_mode;     // UWT_DEPTH_*
   // per-slot strides (elements)
   size_t plane_elems, cand_elems, rec_elems, cnt_elems, tile_elems;
   int grad_tiles_total;  // gradient tiles per slot over all levels
@@ -71,7 +72,21 @@ struct Pools {
   uint32_t* ncand;      // [slot][kMaxLevels]
   uint32_t* cand_xy;    // [slot][cand_elems]   x | y << 16, reference (x-major) order
   uint64_t* rec;        // [slot][rec_elems]    packed records, same order
+  uint16_t* dep;        // [slot][plane_elems]  16-bit depth pyramid (depth modes only)
+  uint16_t* recz;       // [slot][rec_elems]    integer depth of every record (depth modes only)
 };
+
+// The integer depth ObtainCandidatePoints reads for pixel (x, y) of a level (Tracker.cpp:1339,
+// 1344).  REFERENCE mode reproduces depths_[lvl].at<uchar>(y, x) on the CV_16U image: byte x of
+// row y, i.e. the low (x even) or high (x odd) byte of depth pixel x / 2.
+__device__ __forceinline__ int depth_at(const uint16_t* __restrict__ plane, int pitch, int x, int y,
+                                        int depth_mode) {
+  if (depth_mode == UWT_DEPTH_REFERENCE) {
+    const unsigned v = plane[(size_t)y * pitch + (x >> 1)];
+    return (x & 1) ? (int)(v >> 8) : (int)(v & 0xFFu);
+  }
+  return (int)plane[(size_t)y * pitch + x];
+}
 
 struct EstimateIO {
   const int* prev_slots;
@@ -152,6 +167,8 @@ inline LevelRange level_range(const Geom& g, int lo, int hi) {
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
                    size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st,
                    const RemapArgs& rm = RemapArgs());
+int launch_depth_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots,
+                         cudaStream_t st);
 int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, const short2* map1,
                  const uint16_t* map2, int out_w, int out_h, uint8_t* d_dst, cudaStream_t st);
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,

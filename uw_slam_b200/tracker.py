@@ -188,16 +188,21 @@ class Frame:
     def candidatePoints(self, lvl):
         return self._t.get_candidates(self.slot, lvl)
 
+    def depth(self, lvl):
+        return self._t.get_depth(self.slot, lvl)
+
 
 class Tracker:
     """uw::Tracker (include/Tracker.h:90-531), direct photometric path only."""
 
     def __init__(self, depth_available=False, **cfg):
-        if depth_available:
-            raise UwtError(L.E_INVALID, "depth input is out of scope (SURVEY.md 8-f)")
+        # Tracker::Tracker(bool _depth_available), Tracker.cpp:273-277: with depth the candidate
+        # points need depth != 0 and carry Z = depth * 0.0002 (as shipped: the at<uchar> read)
         self._lib = L.load()
         self._h = None
-        self._cfg_overrides = cfg
+        self._cfg_overrides = dict(cfg)
+        if depth_available:
+            self._cfg_overrides.setdefault("depth_mode", L.DEPTH_REFERENCE)
         self.cfg = None
         self._keep = []
 
@@ -268,6 +273,21 @@ class Tracker:
         self._check(self._lib.uwt_upload_frames(self._h, n, p, f.ctypes.data, self._src_w,
                                                 self._src_w * self._src_h))
         return [Frame(self, int(s)) for s in a]
+
+    def AddDepthFrames(self, slots, depth):
+        """System::AddFrame depth part (System.cpp:241-250): u16 array [n, H, W] (or [H, W])."""
+        a, p, n = self._slots(slots)
+        d = np.ascontiguousarray(depth, np.uint16).reshape(n, self.cfg.height, self.cfg.width)
+        self._check(self._lib.uwt_upload_depth_frames(self._h, n, p, d.ctypes.data,
+                                                      self.cfg.width * 2,
+                                                      self.cfg.width * self.cfg.height * 2))
+
+    def get_depth(self, slot, lvl):
+        i = self.level_info(lvl)
+        out = np.empty((i.height, i.width), np.uint16)
+        self._check(self._lib.uwt_get_depth(self._h, slot, lvl,
+                                            out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
 
     def AddFramesHostPtr(self, slots, ptr, row_stride, frame_stride):
         a, p, n = self._slots(slots)
