@@ -152,6 +152,7 @@ __device__ __forceinline__ void patch_img_tile_borders(uint8_t* tile, const Leve
 // count: no shared-memory staging.  A thread reads 32-bit words (4 pixels of one row, coalesced
 // across the warp), compares the four bytes against the threshold at once (SWAR) and adds the
 // 0/1 results into four packed byte counters: a (column, 64-row segment) count is at most 64.
+template <bool kDepth>
 __global__ void __launch_bounds__(256)
 cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
                   const int* __restrict__ slots, int n_slots, int item_begin, int item_count) {
@@ -178,7 +179,7 @@ cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
         w[r] = (gy < L.h) ? __ldg(reinterpret_cast<const uint32_t*>(plane + (size_t)gy * L.pitch + gx))
                           : 0u;
       }
-      if (geom.depth_mode == UWT_DEPTH_NONE) {
+      if constexpr (!kDepth) {
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) acc += __vsetgtu4(w[r], thr4);
       } else {
@@ -257,6 +258,7 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
   if (t == 1023) pools.ncand[(size_t)slot * kMaxLevels + lvl] = warp_tot[31];
 }
 
+template <bool kDepth>
 __global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
                     const int* __restrict__ slots, int n_slots, int item_begin, int item_count) {
@@ -298,9 +300,11 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
     const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
     uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
     uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
-    const bool use_depth = geom.depth_mode != UWT_DEPTH_NONE;
-    const uint16_t* dplane = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off;
-    uint16_t* recz = pools.recz + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
+    constexpr bool use_depth = kDepth;
+    const uint16_t* dplane = kDepth ? pools.dep + (size_t)slot * geom.plane_elems + L.plane_off
+                                    : nullptr;
+    uint16_t* recz =
+        kDepth ? pools.recz + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0) : nullptr;
     // start offsets of this warp's 16 (column, segment) runs: one per lane
     uint32_t my_base = 0;
     {
@@ -352,19 +356,31 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, cand_count_kernel, 256, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, cand_scatter_kernel, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, cand_count_kernel<false>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, cand_scatter_kernel<false>, 256,
+                                                  0);
     if (sms <= 0) sms = 148;
     if (per_sm_count <= 0) per_sm_count = 4;
     if (per_sm_scatter <= 0) per_sm_scatter = 4;
   }
   const int grid_count = (int)std::min<long long>(total, (long long)sms * per_sm_count);
   const int grid_scatter = (int)std::min<long long>(total, (long long)sms * per_sm_scatter);
-  cand_count_kernel<<<grid_count, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin, lr.item_count);
+  const bool depth = g.depth_mode != UWT_DEPTH_NONE;
+  if (depth)
+    cand_count_kernel<true><<<grid_count, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
+                                                        lr.item_count);
+  else
+    cand_count_kernel<false><<<grid_count, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
+                                                         lr.item_count);
   if (cudaGetLastError() != cudaSuccess) return -1;
   cand_scan_kernel<<<dim3(lr.lvl_count, n), 1024, 0, st>>>(g, p, d_slots, lr.lvl_begin);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scatter_kernel<<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin, lr.item_count);
+  if (depth)
+    cand_scatter_kernel<true><<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
+                                                            lr.item_count);
+  else
+    cand_scatter_kernel<false><<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
+                                                             lr.item_count);
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 3;
 }
