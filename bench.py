@@ -487,7 +487,8 @@ def main():
                          "levels (the default does all levels, like the reference)")
     ap.add_argument("--weights", type=int, default=0,
                     help="residual weights: 0 identity (reference), 1 Tukey/MAD, 2 Huber")
-    ap.add_argument("--cpu-sequences", type=int, default=8)
+    ap.add_argument("--cpu-sequences", type=int, default=24,
+                    help="sequences of the workload the single-threaded CPU baseline tracks (~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.out = claim_stdout()

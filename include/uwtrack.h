@@ -54,6 +54,10 @@ extern "C" {
 /* How `deltaMat = A.inv() * b` (src/Tracker.cpp:564) is evaluated. */
 #define UWT_SOLVE_LU 0      /* cv::solve(A, b, DECOMP_LU) -- what cv::MatExpr folds it to */
 #define UWT_SOLVE_INVERSE 1 /* cv::invert(A, DECOMP_LU) followed by the 6x6 * 6x1 gemm    */
+/* North-star option, not in the reference (its "LM_lambda" / ldlt lines are comments,
+ * src/Tracker.cpp:546-549): Levenberg-Marquardt damping A_ii += lm_lambda * A_ii and a float
+ * Cholesky solve; a matrix that is not positive definite gives delta = 0. */
+#define UWT_SOLVE_CHOLESKY_LM 2
 
 /* Residual weights W of the Gauss-Newton step (src/Tracker.cpp:495-496). */
 #define UWT_WEIGHT_IDENTITY 0 /* IdentityWeights: what the reference ships (Tracker.cpp:495)    */
@@ -108,6 +112,7 @@ typedef struct {
   int weight_mode;           /* UWT_WEIGHT_* (0 = reference)                             */
   float huber_delta;         /* UWT_WEIGHT_HUBER threshold in gray levels                */
   int depth_mode;            /* UWT_DEPTH_* (0 = mono, the reference's default run mode)  */
+  float lm_lambda;           /* UWT_SOLVE_CHOLESKY_LM damping (0.2 in the reference's comment) */
 } uwt_config;
 
 typedef struct {

@@ -332,6 +332,7 @@ void uwo_default_params(uwo_params* p) {
   p->threads = 1;
   p->weight_mode = UWO_WEIGHT_IDENTITY;  // Tracker.cpp:495
   p->huber_delta = 10.0f;
+  p->lm_lambda = 0.2f;  // the value in the reference's commented DSO-way block, Tracker.cpp:546
 }
 
 void uwo_pyr_down(const uint8_t* src, int w, int h, uint8_t* dst) {
@@ -528,6 +529,37 @@ int uwo_lu_solve6(const float* A36, const float* b6, float* x6) {
     return 0;
   }
   std::memcpy(x6, B, sizeof(B));
+  return 1;
+}
+
+int uwo_cholesky_lm_solve6(const float* A36, const float* b6, float lambda, float* x6) {
+  // ARITHMETIC.md S2: A_ii + lambda * A_ii, L L^T by columns, then L y = b and L^T x = y;
+  // every float operation rounded on its own, sums left to right
+  float L[36];
+  for (int i = 0; i < 6; ++i) x6[i] = 0.0f;
+  for (int j = 0; j < 6; ++j) {
+    float s = A36[j * 6 + j] + lambda * A36[j * 6 + j];
+    for (int k = 0; k < j; ++k) s = s - L[j * 6 + k] * L[j * 6 + k];
+    if (!(s > 0.0f)) return 0;
+    const float d = std::sqrt(s);
+    L[j * 6 + j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      float t = A36[i * 6 + j];
+      for (int k = 0; k < j; ++k) t = t - L[i * 6 + k] * L[j * 6 + k];
+      L[i * 6 + j] = t / d;
+    }
+  }
+  float y[6];
+  for (int i = 0; i < 6; ++i) {
+    float t = b6[i];
+    for (int k = 0; k < i; ++k) t = t - L[i * 6 + k] * y[k];
+    y[i] = t / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    float t = y[i];
+    for (int k = i + 1; k < 6; ++k) t = t - L[k * 6 + i] * x6[k];
+    x6[i] = t / L[i * 6 + i];
+  }
   return 1;
 }
 
@@ -852,7 +884,10 @@ int uwo_gn_update(const uwo_params* p, const double* sums32, int k, float* pose7
     for (int a = 0; a < 6; ++a) b[a] = (float)(-sums32[21 + a]);
   }
   // Tracker.cpp:564: deltaMat = A.inv() * b
-  if (p->solve_mode == UWO_SOLVE_LU) {
+  if (p->solve_mode == UWO_SOLVE_CHOLESKY_LM) {
+    if (!uwo_cholesky_lm_solve6(A, b, p->lm_lambda, delta))
+      for (int i = 0; i < 6; ++i) delta[i] = 0.0f;
+  } else if (p->solve_mode == UWO_SOLVE_LU) {
     uwo_lu_solve6(A, b, delta);
   } else {
     float Ainv[36];

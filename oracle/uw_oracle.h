@@ -26,6 +26,7 @@ extern "C" {
 /* solve_mode: how `A.inv() * b` (Tracker.cpp:564) is evaluated. */
 #define UWO_SOLVE_LU 0      /* cv::solve(A,b,DECOMP_LU): what OpenCV's MatExpr does */
 #define UWO_SOLVE_INVERSE 1 /* cv::invert(A) then gemm: the literal reading         */
+#define UWO_SOLVE_CHOLESKY_LM 2 /* north-star option: LM damping + float Cholesky (ARITHMETIC S2) */
 
 /* weight_mode: residual weights W of the Gauss-Newton step (Tracker.cpp:495-496). */
 #define UWO_WEIGHT_IDENTITY 0 /* IdentityWeights: what the reference ships (Tracker.cpp:495)  */
@@ -53,6 +54,7 @@ typedef struct {
   int threads;                /* 1 = like the reference; >1 = std::thread over points  */
   int weight_mode;            /* UWO_WEIGHT_* (Tracker.cpp:495-496)                */
   float huber_delta;          /* UWO_WEIGHT_HUBER threshold in gray levels         */
+  float lm_lambda;            /* UWO_SOLVE_CHOLESKY_LM damping                      */
 } uwo_params;
 
 /* One record per Gauss-Newton iteration (including the breaking one). */
@@ -129,6 +131,8 @@ void uwo_huber_weights(const float* v, int n, float delta, float* w);
  * (normalising constructor, se3.hpp:446-448), out = previous * current. */
 void uwo_chain_pose(const float* previous7, const float* rigid7, float scale, float* out7);
 
+/* LM-damped float Cholesky solve (north-star option).  Returns 0 if not positive definite. */
+int uwo_cholesky_lm_solve6(const float* A36, const float* b6, float lambda, float* x6);
 /* cv::solve / cv::invert (DECOMP_LU) on 6x6 f32.  Return 0 if singular. */
 int uwo_lu_solve6(const float* A36, const float* b6, float* x6);
 int uwo_lu_invert6(const float* A36, float* Ainv36);

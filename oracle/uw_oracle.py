@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libuw_oracle.so")
 MAX_LEVELS = 8
-SOLVE_LU, SOLVE_INVERSE = 0, 1
+SOLVE_LU, SOLVE_INVERSE, SOLVE_CHOLESKY_LM = 0, 1, 2
 ACCUM_DOUBLE, ACCUM_LONGDOUBLE = 0, 1
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16 = 0, 1, 2
@@ -26,7 +26,7 @@ class Params(C.Structure):
         ("max_iterations", C.c_int), ("epsilon", C.c_float), ("residual_scale", C.c_float),
         ("gradient_threshold", C.c_double),
         ("solve_mode", C.c_int), ("accum_mode", C.c_int), ("threads", C.c_int),
-        ("weight_mode", C.c_int), ("huber_delta", C.c_float),
+        ("weight_mode", C.c_int), ("huber_delta", C.c_float), ("lm_lambda", C.c_float),
     ]
 
 
@@ -300,6 +300,17 @@ def lu_solve6(A, b):
     b = np.ascontiguousarray(b, np.float32)
     x = np.empty(6, np.float32)
     ok = lib().uwo_lu_solve6(_p(A, C.c_float), _p(b, C.c_float), _p(x, C.c_float))
+    return x, ok
+
+
+def cholesky_lm_solve6(A, b, lam):
+    A = np.ascontiguousarray(A, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    x = np.empty(6, np.float32)
+    f = lib().uwo_cholesky_lm_solve6
+    f.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+    f.restype = C.c_int
+    ok = f(_p(A, C.c_float), _p(b, C.c_float), float(lam), _p(x, C.c_float))
     return x, ok
 
 

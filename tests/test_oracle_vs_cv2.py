@@ -230,3 +230,24 @@ def test_huber_weights(oracle):
         with np.errstate(divide="ignore"):
             ref = np.where(a <= np.float32(d), np.float32(1), np.float32(d) / a).astype(np.float32)
         assert np.array_equal(oracle.huber_weights(v, d), ref)
+
+
+def test_cholesky_lm_solver(oracle):
+    # north-star solver option (ARITHMETIC.md S2): against an fp64 solve of the damped system,
+    # and against cv2.solve(DECOMP_CHOLESKY) for lambda = 0
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        J = rng.normal(size=(40, 6)).astype(np.float32)
+        A = (J.T @ J).astype(np.float32)
+        b = rng.normal(size=6).astype(np.float32)
+        for lam in (0.0, 0.2, 3.0):
+            x, ok = oracle.cholesky_lm_solve6(A, b, lam)
+            assert ok == 1
+            Ad = A.astype(np.float64) + lam * np.diag(np.diag(A).astype(np.float64))
+            ref = np.linalg.solve(Ad, b.astype(np.float64))
+            assert np.abs(x - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+        ok_cv, xc = cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_CHOLESKY)
+        x0, _ = oracle.cholesky_lm_solve6(A, b, 0.0)
+        assert ok_cv and np.abs(x0 - xc.ravel()).max() <= 1e-4 * max(1.0, np.abs(xc).max())
+    x, ok = oracle.cholesky_lm_solve6(-np.eye(6, dtype=np.float32), np.ones(6, np.float32), 0.2)
+    assert ok == 0 and not x.any()

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("UWT_LIBRARY") or os.path.join(HERE, "libuwtrack.so")
 MAX_LEVELS = 7
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
-SOLVE_LU, SOLVE_INVERSE = 0, 1
+SOLVE_LU, SOLVE_INVERSE, SOLVE_CHOLESKY_LM = 0, 1, 2
 FLAG_TRACE = 1
 FLAG_DMMA_ACCUM = 2
 FLAG_CLUSTER_KERNEL = 4
@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("gradient_threshold", C.c_double), ("solve_mode", C.c_int), ("device", C.c_int),
         ("max_frames", C.c_int), ("cluster_size", C.c_int), ("flags", C.c_uint),
         ("weight_mode", C.c_int), ("huber_delta", C.c_float), ("depth_mode", C.c_int),
+        ("lm_lambda", C.c_float),
     ]
 
 

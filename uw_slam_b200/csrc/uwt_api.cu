@@ -173,6 +173,7 @@ int build_geom(const uwt_config& c, Geom& g) {
   g.residual_scale = c.residual_scale;
   g.gradient_threshold = c.gradient_threshold;
   g.solve_mode = c.solve_mode;
+  g.lm_lambda = c.lm_lambda;
   g.weight_mode = c.weight_mode;
   g.huber_delta = c.huber_delta;
   g.depth_mode = c.depth_mode;
@@ -338,6 +339,7 @@ int uwt_default_config(uwt_config* cfg) {
   cfg->weight_mode = UWT_WEIGHT_IDENTITY;  // Tracker.cpp:495
   cfg->huber_delta = 10.0f;
   cfg->depth_mode = UWT_DEPTH_NONE;  // Tracker(depth_available = false), System.cpp:121
+  cfg->lm_lambda = 0.2f;             // "float LM_lambda = 0.2" in the comment at Tracker.cpp:546
   return UWT_OK;
 }
 
@@ -364,7 +366,10 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
                 c.last_level);
   if (c.max_iterations < 1 || c.max_frames < 1)
     return fail(nullptr, UWT_E_INVALID, "max_iterations and max_frames must be >= 1");
-  if (c.solve_mode != UWT_SOLVE_LU && c.solve_mode != UWT_SOLVE_INVERSE)
+  if (c.solve_mode == UWT_SOLVE_CHOLESKY_LM && !(c.lm_lambda >= 0.0f))
+    return fail(nullptr, UWT_E_INVALID, "lm_lambda must be >= 0");
+  if (c.solve_mode != UWT_SOLVE_LU && c.solve_mode != UWT_SOLVE_INVERSE &&
+      c.solve_mode != UWT_SOLVE_CHOLESKY_LM)
     return fail(nullptr, UWT_E_INVALID, "bad solve_mode %d", c.solve_mode);
   if (c.weight_mode < UWT_WEIGHT_IDENTITY || c.weight_mode > UWT_WEIGHT_HUBER)
     return fail(nullptr, UWT_E_INVALID, "bad weight_mode %d", c.weight_mode);

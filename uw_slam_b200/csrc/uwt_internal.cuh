@@ -52,6 +52,7 @@ struct Geom {
   float epsilon, residual_scale;
   double gradient_threshold;
   int solve_mode;
+  float lm_lambda;    // UWT_SOLVE_CHOLESKY_LM damping
   int weight_mode;    // UWT_WEIGHT_*
   float huber_delta;
   int depth_mode;     // UWT_DEPTH_*
