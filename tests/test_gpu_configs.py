@@ -122,3 +122,52 @@ def test_rejected_configurations():
         w, h = cfg.pop("width", 640), cfg.pop("height", 480)
         with pytest.raises(U.UwtError):
             U.Tracker(False).InitializePyramid(w, h, K, **cfg)
+
+
+def test_randomised_small_configurations(oracle):
+    """Seeded random sweep over frame sizes (every multiple of 16 the level count allows), level
+    ranges, thresholds and weight / solve modes on noise-plus-structure images: image kernels,
+    candidate lists and the whole estimate against the oracle."""
+    import uw_slam_b200 as U
+    rng = np.random.default_rng(2024)
+    for case in range(48):
+        levels = int(rng.integers(1, 6))
+        mult = max(16, 1 << (levels - 1))
+        lo = max(2 << (levels - 1), mult)           # coarsest level at least 2 x 2
+        w = int(rng.integers(lo // mult, 384 // mult + 1)) * mult
+        hm = max(2, 1 << (levels - 1))              # the reference requires even sizes
+        h = int(rng.integers(max(1, (2 << (levels - 1)) // hm), 320 // hm + 1)) * hm
+        first = int(rng.integers(0, levels))
+        last = int(rng.integers(0, first + 1))
+        cfg = dict(gradient_threshold=float(rng.choice([2.0, 11.5, 20.0, 35.0])),
+                   max_iterations=int(rng.choice([1, 4, 50])),
+                   solve_mode=int(rng.integers(0, 3)), weight_mode=int(rng.integers(0, 3)),
+                   huber_delta=float(rng.choice([2.5, 9.0])))
+        fx, fy = float(rng.uniform(0.6, 1.4) * w), float(rng.uniform(0.6, 1.4) * w)
+        cx, cy = w / 2 + float(rng.normal(0, 3)), h / 2 + float(rng.normal(0, 3))
+        ys, xs = np.mgrid[0:h, 0:w]
+        base = 120 + 70 * np.sin(xs * rng.uniform(0.05, 0.4)) * np.cos(ys * rng.uniform(0.05, 0.4))
+        prev = np.clip(base + rng.integers(-25, 25, (h, w)), 0, 255).astype(np.uint8)
+        cur = np.clip(np.roll(base, (int(rng.integers(-1, 2)), int(rng.integers(-1, 2))), (0, 1)) +
+                      rng.integers(-25, 25, (h, w)), 0, 255).astype(np.uint8)
+        t = U.Tracker(False)
+        t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                            max_frames=2, levels=levels, first_level=first, last_level=last, **cfg)
+        fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+        t.ApplyGradient(fp)
+        t.ObtainCandidatePoints(fp)
+        pose = t.EstimatePose(fp, fc)[0]
+        rp = oracle.FrameData(prev, levels=levels, gradient_threshold=cfg["gradient_threshold"])
+        rc = oracle.FrameData(cur, levels=levels, with_candidates=False)
+        tag = (case, w, h, levels, first, last, cfg)
+        for lvl in range(levels):
+            assert np.array_equal(fp.image(lvl), rp.images[lvl]), tag
+            gx, gy, g = fp.gradients(lvl)
+            assert np.array_equal(gx, rp.gx[lvl]) and np.array_equal(gy, rp.gy[lvl]), tag
+            assert np.array_equal(g, rp.g[lvl]), tag
+            assert np.array_equal(fp.candidatePoints(lvl), rp.cand[lvl]), tag
+        okw = {k: v for k, v in cfg.items() if k != "gradient_threshold"}
+        p = oracle.default_params(w, h, fx, fy, cx, cy, levels=levels, first_level=first,
+                                  last_level=last, **okw)
+        assert np.array_equal(pose, oracle.estimate_pose(p, rp, rc)[0]), tag
+        t.close()
