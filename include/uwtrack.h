@@ -75,6 +75,15 @@ extern "C" {
                                  BYTE x of row y (low / high byte of depth pixel x/2)             */
 #define UWT_DEPTH_U16 2       /* what the code evidently means: at<ushort>(y,x)                   */
 
+/* Derivative stencil of Tracker::ApplyGradient (src/Tracker.cpp:1133-1134). */
+#define UWT_GRADIENT_SCHARR 0 /* cv::Scharr, the reference                                        */
+#define UWT_GRADIENT_SOBEL 1  /* cv::Sobel(ksize = 3), the north-star wording; not the reference  */
+
+/* How the target image is sampled at the warped position (src/Tracker.cpp:472). */
+#define UWT_SAMPLE_NEAREST 0  /* image2.at<uchar>(round(y2), round(x2)), the reference            */
+#define UWT_SAMPLE_BILINEAR 1 /* north-star wording: float interpolation of the four neighbours;
+                                 identity weights, mono input, cluster kernel                    */
+
 /* cfg.flags */
 #define UWT_FLAG_TRACE 1u /* record a per-iteration trace (uwt_get_trace); debugging/parity */
 /* A/B switch: hold the 8x8 Gram accumulator [J | 50r]^T [J | 50r] in fp64 tensor-core (DMMA
@@ -113,6 +122,8 @@ typedef struct {
   float huber_delta;         /* UWT_WEIGHT_HUBER threshold in gray levels                */
   int depth_mode;            /* UWT_DEPTH_* (0 = mono, the reference's default run mode)  */
   float lm_lambda;           /* UWT_SOLVE_CHOLESKY_LM damping (0.2 in the reference's comment) */
+  int gradient_op;           /* UWT_GRADIENT_* (0 = Scharr, the reference)               */
+  int sampling;              /* UWT_SAMPLE_* (0 = nearest, the reference)                */
 } uwt_config;
 
 typedef struct {

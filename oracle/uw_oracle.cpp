@@ -333,6 +333,7 @@ void uwo_default_params(uwo_params* p) {
   p->weight_mode = UWO_WEIGHT_IDENTITY;  // Tracker.cpp:495
   p->huber_delta = 10.0f;
   p->lm_lambda = 0.2f;  // the value in the reference's commented DSO-way block, Tracker.cpp:546
+  p->sampling = 0;      // Tracker.cpp:472: nearest
 }
 
 void uwo_pyr_down(const uint8_t* src, int w, int h, uint8_t* dst) {
@@ -361,6 +362,22 @@ void uwo_scharr(const uint8_t* img, int w, int h, int16_t* gx, int16_t* gy) {
       const int vy = 3 * (rp[xm] - rm[xm]) + 10 * (rp[x] - rm[x]) + 3 * (rp[xp] - rm[xp]);
       gx[(size_t)y * w + x] = (int16_t)vx;
       gy[(size_t)y * w + x] = (int16_t)vy;
+    }
+  }
+}
+
+void uwo_sobel(const uint8_t* img, int w, int h, int16_t* gx, int16_t* gy) {
+  auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+  for (int y = 0; y < h; ++y) {
+    const uint8_t* rm = img + (size_t)refl(y - 1, h) * w;
+    const uint8_t* r0 = img + (size_t)y * w;
+    const uint8_t* rp = img + (size_t)refl(y + 1, h) * w;
+    for (int x = 0; x < w; ++x) {
+      const int xm = refl(x - 1, w), xp = refl(x + 1, w);
+      gx[(size_t)y * w + x] =
+          (int16_t)((rm[xp] - rm[xm]) + 2 * (r0[xp] - r0[xm]) + (rp[xp] - rp[xm]));
+      gy[(size_t)y * w + x] =
+          (int16_t)((rp[xm] - rm[xm]) + 2 * (rp[x] - rm[x]) + (rp[xp] - rm[xp]));
     }
   }
 }
@@ -786,16 +803,29 @@ int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8
         const int i1 = I1[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:471
         const int i2 = I2[(size_t)yi * cols + xi];            // Tracker.cpp:472
         const int r = i2 - i1;                                // Tracker.cpp:474
+        float rf = (float)r;
+        if (p->sampling == 1) {
+          // north-star option (ARITHMETIC.md B1): float bilinear interpolation at (x2, y2)
+          const int ix = (int)x2, iy = (int)y2;
+          const float ax = x2 - (float)ix, ay = y2 - (float)iy;
+          const int ix1 = ix + 1 > cols - 1 ? cols - 1 : ix + 1;
+          const int iy1 = iy + 1 > rows - 1 ? rows - 1 : iy + 1;
+          const float a = I2[(size_t)iy * cols + ix], b = I2[(size_t)iy * cols + ix1];
+          const float c = I2[(size_t)iy1 * cols + ix], d = I2[(size_t)iy1 * cols + ix1];
+          const float top = a + ax * (b - a), bot = c + ax * (d - c);
+          const float v = top + ay * (bot - top);
+          rf = v - (float)i1;
+        }
         const float jlx = gx[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:476
         const float jly = gy[(size_t)(int)y1 * cols + (int)x1];  // Tracker.cpp:477
         // Jl * Jw (Tracker.cpp:479) is cv::gemm: double accumulators, one rounding
         for (int q = 0; q < 6; ++q)
           J[(size_t)i * 6 + q] =
               (float)((double)jlx * (double)Jw0[q] + (double)jly * (double)Jw1[q]);
-        res[i] = (float)r;                      // Residuals row, Tracker.cpp:487
-        r50[i] = (float)r * p->residual_scale;  // Tracker.cpp:559 (exact)
+        res[i] = rf;                         // Residuals row, Tracker.cpp:487
+        r50[i] = rf * p->residual_scale;     // Tracker.cpp:559 (exact for integer residuals)
         valid[i] = 1;
-        sum_r2 += (long long)r * r;
+        if (p->sampling == 0) sum_r2 += (long long)r * r;
         ++n_valid;
       }
     }
@@ -809,6 +839,13 @@ int uwo_sweep_range(const uwo_params* p, int lvl, const uint8_t* I1, const uint8
     n_valid += part_nv[c];
   }
   for (int i = 0; i < 32; ++i) sums32[i] = 0.0;
+  if (p->sampling == 1 && p->weight_mode == UWO_WEIGHT_IDENTITY) {
+    // float residuals: error = inv_num * Residuals^T Residuals with the fp64 accumulation of U3
+    long double esum = 0.0L;
+    for (int i = 0; i < n; ++i)
+      if (valid[i]) esum += (long double)((double)res[i] * (double)res[i]);
+    sums32[29] = (double)esum;
+  }
   if (p->weight_mode != UWO_WEIGHT_IDENTITY) {
     // Tracker.cpp:496: W = TukeyFunctionWeights(Residuals) on the valid rows only, in order
     std::vector<float> rv, wv;
@@ -862,7 +899,7 @@ int uwo_gn_update(const uwo_params* p, const double* sums32, int k, float* pose7
   }
   // Tracker.cpp:499-502: error = (1/N) r^T r  (U3)
   const float inv_num = 1.0 / n_valid;
-  const float error = (p->weight_mode == UWO_WEIGHT_IDENTITY)
+  const float error = (p->weight_mode == UWO_WEIGHT_IDENTITY && p->sampling == 0)
                           ? (float)((double)inv_num * (double)sum_r2)
                           : (float)((double)inv_num * sums32[29]);
   if (tr) tr->error = error;
@@ -949,7 +986,7 @@ int uwo_estimate_pose(const uwo_params* p, const uint8_t* const* prev_images,
       if (stats && sums[28] > 0) {
         const float inv_num = 1.0 / (int)sums[28];
         stats->final_error[lvl] =
-            (p->weight_mode == UWO_WEIGHT_IDENTITY)
+            (p->weight_mode == UWO_WEIGHT_IDENTITY && p->sampling == 0)
                 ? (float)((double)inv_num * (double)(long long)sums[27])
                 : (float)((double)inv_num * sums[29]);
         if (!brk) stats->iterations[lvl] = k + 1;

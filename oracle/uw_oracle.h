@@ -55,6 +55,7 @@ typedef struct {
   int weight_mode;            /* UWO_WEIGHT_* (Tracker.cpp:495-496)                */
   float huber_delta;          /* UWO_WEIGHT_HUBER threshold in gray levels         */
   float lm_lambda;            /* UWO_SOLVE_CHOLESKY_LM damping                      */
+  int sampling;               /* 0 nearest (Tracker.cpp:472), 1 bilinear (north-star, B1) */
 } uwo_params;
 
 /* One record per Gauss-Newton iteration (including the breaking one). */
@@ -83,6 +84,8 @@ void uwo_default_params(uwo_params* p);
 void uwo_pyr_down(const uint8_t* src, int w, int h, uint8_t* dst);
 /* Tracker::ApplyGradient, Tracker.cpp:1133-1134: Scharr 16S, BORDER_REFLECT_101. */
 void uwo_scharr(const uint8_t* img, int w, int h, int16_t* gx, int16_t* gy);
+/* north-star wording: cv::Sobel(img, CV_16S, 1, 0 / 0, 1, 3), BORDER_REFLECT_101 (not the reference) */
+void uwo_sobel(const uint8_t* img, int w, int h, int16_t* gx, int16_t* gy);
 /* Tracker.cpp:1139-1142: convertScaleAbs x2 + addWeighted(.5,.5). */
 void uwo_gradmag(const int16_t* gx, const int16_t* gy, long long n, uint8_t* g);
 /* Tracker::ObtainCandidatePoints, Tracker.cpp:1314-1357 (mono branch).  pts4 must

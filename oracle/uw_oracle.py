@@ -27,6 +27,7 @@ class Params(C.Structure):
         ("gradient_threshold", C.c_double),
         ("solve_mode", C.c_int), ("accum_mode", C.c_int), ("threads", C.c_int),
         ("weight_mode", C.c_int), ("huber_delta", C.c_float), ("lm_lambda", C.c_float),
+        ("sampling", C.c_int),
     ]
 
 
@@ -211,6 +212,19 @@ def scharr(img):
     return gx, gy
 
 
+def sobel(img):
+    h, w = img.shape
+    img = np.ascontiguousarray(img, np.uint8)
+    gx = np.empty((h, w), np.int16)
+    gy = np.empty((h, w), np.int16)
+    f = lib().uwo_sobel
+    f.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_int16),
+                  C.POINTER(C.c_int16)]
+    f.restype = None
+    f(_p(img, C.c_uint8), w, h, _p(gx, C.c_int16), _p(gy, C.c_int16))
+    return gx, gy
+
+
 def gradmag(gx, gy):
     gx = np.ascontiguousarray(gx, np.int16)
     gy = np.ascontiguousarray(gy, np.int16)
@@ -352,7 +366,7 @@ class FrameData:
     """What uw::Frame holds after pyramid + ApplyGradient + ObtainCandidatePoints."""
 
     def __init__(self, img, levels=5, gradient_threshold=20.0, with_candidates=True, depth=None,
-                 depth_mode=DEPTH_NONE):
+                 depth_mode=DEPTH_NONE, gradient_op=0):
         self.images = build_pyramid(img, levels)
         self.gx, self.gy, self.g, self.cand, self.mean, self.ithr = [], [], [], [], [], []
         self.depths, self.zsrc = [], []
@@ -362,7 +376,7 @@ class FrameData:
                 self.depths.append(depth_pyr_down(self.depths[-1]))
         if with_candidates:
             for lvl, im in enumerate(self.images):
-                gx, gy = scharr(im)
+                gx, gy = sobel(im) if gradient_op == 1 else scharr(im)
                 g = gradmag(gx, gy)
                 c, m, t = candidates(g, gradient_threshold)
                 if self.depths:

@@ -26,12 +26,13 @@ def run_case(oracle, w, h, seed, levels, first, last, batch=1, **cfg):
     poses, stats = t.EstimatePose(fp, fc, return_stats=True)
     okw = {k: v for k, v in cfg.items() if k in ("max_iterations", "epsilon", "residual_scale",
                                                  "gradient_threshold", "solve_mode",
-                                                 "weight_mode", "huber_delta", "lm_lambda")}
+                                                 "weight_mode", "huber_delta", "lm_lambda", "sampling")}
+    gop = cfg.get("gradient_op", 0)
     p = oracle.default_params(w, h, fx, fy, cx, cy, levels=levels, first_level=first,
                               last_level=last, **okw)
     thr = cfg.get("gradient_threshold", 20.0)
     for i in range(batch):
-        rp = oracle.FrameData(pairs[i][0], levels=levels, gradient_threshold=thr)
+        rp = oracle.FrameData(pairs[i][0], levels=levels, gradient_threshold=thr, gradient_op=gop)
         rc = oracle.FrameData(pairs[i][1], levels=levels, with_candidates=False)
         if i == 0:
             for lvl in range(levels):
@@ -66,6 +67,10 @@ def test_level_configurations(oracle, levels, first, last):
                                  dict(gradient_threshold=5.0), dict(gradient_threshold=60.5),
                                  dict(gradient_threshold=400.0),   # nothing passes: U2 everywhere
                                  dict(solve_mode=1, weight_mode=1),
+                                 dict(gradient_op=1), dict(gradient_op=1, weight_mode=1),
+                                 dict(sampling=1), dict(sampling=1, residual_scale=12.5),
+                                 # the north-star wording end to end: Sobel, bilinear, LM/Cholesky
+                                 dict(sampling=1, gradient_op=1, solve_mode=2, lm_lambda=0.2),
                                  dict(solve_mode=2), dict(solve_mode=2, lm_lambda=0.0),
                                  dict(solve_mode=2, lm_lambda=7.5, weight_mode=2),
                                  dict(weight_mode=2, huber_delta=3.0, residual_scale=20.0)])
@@ -74,7 +79,8 @@ def test_parameter_variations(oracle, cfg):
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(levels=4, first=3, last=0),
-                                 dict(extra=dict(solve_mode=2, lm_lambda=0.2))])
+                                 dict(extra=dict(solve_mode=2, lm_lambda=0.2)),
+                                 dict(extra=dict(sampling=1))])   # cluster kernel, batch of 32
 def test_dataflow_kernel_configurations(oracle, cfg):
     # 32 problems -> the dataflow kernel; non-default level ranges and the LM/Cholesky solver
     run_case(oracle, 160, 128, 40, cfg.get("levels", 5), cfg.get("first", 4), cfg.get("last", 1),
@@ -117,6 +123,7 @@ def test_rejected_configurations():
                 dict(levels=0), dict(levels=8), dict(first_level=5), dict(last_level=-1),
                 dict(first_level=1, last_level=2), dict(max_iterations=0), dict(max_frames=0),
                 dict(solve_mode=3), dict(solve_mode=2, lm_lambda=-1.0), dict(cluster_size=3),
+                dict(gradient_op=2), dict(sampling=2), dict(sampling=1, weight_mode=1),
                 dict(device=99)):
         cfg = dict(bad)
         w, h = cfg.pop("width", 640), cfg.pop("height", 480)

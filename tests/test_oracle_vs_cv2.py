@@ -251,3 +251,12 @@ def test_cholesky_lm_solver(oracle):
         assert ok_cv and np.abs(x0 - xc.ravel()).max() <= 1e-4 * max(1.0, np.abs(xc).max())
     x, ok = oracle.cholesky_lm_solve6(-np.eye(6, dtype=np.float32), np.ones(6, np.float32), 0.2)
     assert ok == 0 and not x.any()
+
+
+@pytest.mark.parametrize("w,h", SIZES[:3])
+def test_sobel_option_matches_cv(oracle, w, h):
+    # north-star wording (Sobel); the reference itself uses Scharr (Tracker.cpp:1133-1134)
+    img = rand_img(np.random.default_rng(w * 3 + h), w, h)
+    gx, gy = oracle.sobel(img)
+    assert np.array_equal(gx, cv2.Sobel(img, cv2.CV_16S, 1, 0, ksize=3))
+    assert np.array_equal(gy, cv2.Sobel(img, cv2.CV_16S, 0, 1, ksize=3))

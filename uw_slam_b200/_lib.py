@@ -17,6 +17,8 @@ FLAG_CLUSTER_KERNEL = 4
 FLAG_LAZY_LEVELS = 8
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16 = 0, 1, 2
+GRADIENT_SCHARR, GRADIENT_SOBEL = 0, 1
+SAMPLE_NEAREST, SAMPLE_BILINEAR = 0, 1
 KERNEL_CLASSES = ("pyramid", "gradient", "candidates", "estimate")
 
 
@@ -29,7 +31,8 @@ class Config(C.Structure):
         ("gradient_threshold", C.c_double), ("solve_mode", C.c_int), ("device", C.c_int),
         ("max_frames", C.c_int), ("cluster_size", C.c_int), ("flags", C.c_uint),
         ("weight_mode", C.c_int), ("huber_delta", C.c_float), ("depth_mode", C.c_int),
-        ("lm_lambda", C.c_float),
+        ("lm_lambda", C.c_float), ("gradient_op", C.c_int),
+        ("sampling", C.c_int),
     ]
 
 

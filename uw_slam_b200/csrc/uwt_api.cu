@@ -177,6 +177,8 @@ int build_geom(const uwt_config& c, Geom& g) {
   g.weight_mode = c.weight_mode;
   g.huber_delta = c.huber_delta;
   g.depth_mode = c.depth_mode;
+  g.gradient_op = c.gradient_op;
+  g.sampling = c.sampling;
   size_t plane = 0, cand = 0, rec = 0, cnt = 0;
   int tiles = 0, items = 0;
   // Tracker::InitializePyramid, Tracker.cpp:297-340 (same expression types as the source:
@@ -340,6 +342,8 @@ int uwt_default_config(uwt_config* cfg) {
   cfg->huber_delta = 10.0f;
   cfg->depth_mode = UWT_DEPTH_NONE;  // Tracker(depth_available = false), System.cpp:121
   cfg->lm_lambda = 0.2f;             // "float LM_lambda = 0.2" in the comment at Tracker.cpp:546
+  cfg->gradient_op = UWT_GRADIENT_SCHARR;  // Tracker.cpp:1133
+  cfg->sampling = UWT_SAMPLE_NEAREST;      // Tracker.cpp:472
   return UWT_OK;
 }
 
@@ -375,6 +379,15 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
     return fail(nullptr, UWT_E_INVALID, "bad weight_mode %d", c.weight_mode);
   if (c.weight_mode == UWT_WEIGHT_HUBER && !(c.huber_delta > 0.0f))
     return fail(nullptr, UWT_E_INVALID, "huber_delta must be > 0");
+  if (c.sampling != UWT_SAMPLE_NEAREST && c.sampling != UWT_SAMPLE_BILINEAR)
+    return fail(nullptr, UWT_E_INVALID, "bad sampling %d", c.sampling);
+  if (c.sampling == UWT_SAMPLE_BILINEAR &&
+      (c.weight_mode != UWT_WEIGHT_IDENTITY || c.depth_mode != UWT_DEPTH_NONE ||
+       (c.flags & UWT_FLAG_DMMA_ACCUM)))
+    return fail(nullptr, UWT_E_INVALID,
+                "bilinear sampling supports identity weights, mono input, register accumulator");
+  if (c.gradient_op != UWT_GRADIENT_SCHARR && c.gradient_op != UWT_GRADIENT_SOBEL)
+    return fail(nullptr, UWT_E_INVALID, "bad gradient_op %d", c.gradient_op);
   if (c.depth_mode < UWT_DEPTH_NONE || c.depth_mode > UWT_DEPTH_U16)
     return fail(nullptr, UWT_E_INVALID, "bad depth_mode %d", c.depth_mode);
   if (c.depth_mode != UWT_DEPTH_NONE &&
@@ -821,7 +834,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
     const LevelGeom& Lf = t->geom.lv[t->cfg.last_level];
     if (n == 1 && t->cfg.cluster_size == 0 && !(t->cfg.flags & UWT_FLAG_TRACE) &&
         t->cfg.weight_mode == UWT_WEIGHT_IDENTITY && t->cfg.depth_mode == UWT_DEPTH_NONE &&
-        (long long)Lf.w * Lf.h >= (1 << 20)) {
+        t->cfg.sampling == UWT_SAMPLE_NEAREST && (long long)Lf.w * Lf.h >= (1 << 20)) {
       ShardState s;
       std::memset(&s, 0, sizeof(s));
       const float ident[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
@@ -890,6 +903,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
                         t->cfg.cluster_size == 0 &&
                         t->cfg.weight_mode == UWT_WEIGHT_IDENTITY &&
                         t->cfg.depth_mode == UWT_DEPTH_NONE &&
+                        t->cfg.sampling == UWT_SAMPLE_NEAREST &&
                         !(t->cfg.flags & (UWT_FLAG_DMMA_ACCUM | UWT_FLAG_CLUSTER_KERNEL));
   if (use_flow) {
     const size_t need = flow_workspace_bytes(t->geom, n);
@@ -959,8 +973,10 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
   if ((rc = check_slots(t, 1, &cur_slot))) return rc;
   if (nranks < 1 || rank < 0 || rank >= nranks)
     return fail(t, UWT_E_INVALID, "bad shard rank %d of %d", rank, nranks);
-  if (t->cfg.weight_mode != UWT_WEIGHT_IDENTITY || t->cfg.depth_mode != UWT_DEPTH_NONE)
-    return fail(t, UWT_E_INVALID, "the sharded mode supports identity weights, mono input only");
+  if (t->cfg.weight_mode != UWT_WEIGHT_IDENTITY || t->cfg.depth_mode != UWT_DEPTH_NONE ||
+      t->cfg.sampling != UWT_SAMPLE_NEAREST)
+    return fail(t, UWT_E_INVALID,
+                "the sharded mode supports identity weights, mono input, nearest sampling only");
   if (!t->slots[prev_slot].candidates)
     return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slot);
   if (!t->slots[cur_slot].pyramid) return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slot);

@@ -107,15 +107,16 @@ __device__ __forceinline__ uint32_t window_at(const uint8_t* tile, int off) {
   return __funnelshift_r(p[0], p[1], 8 * (off & 3));
 }
 __device__ __forceinline__ void scharr_from_tile(const uint8_t* tile, int x0, int y0, int x, int y,
-                                                 int& gx, int& gy, int& center) {
+                                                 const StencilWeights& sw, int& gx, int& gy,
+                                                 int& center) {
   // byte offset of pixel (x - 1, y - 1) inside the tile
   const int off = (y - y0) * kImgTilePitch + (x - x0 + 3);
   const uint32_t top = window_at(tile, off);
   const uint32_t mid = window_at(tile, off + kImgTilePitch);
   const uint32_t bot = window_at(tile, off + 2 * kImgTilePitch);
   center = (mid >> 8) & 0xFF;
-  gx = dp4a_us(top, 0x000300FDu, dp4a_us(mid, 0x000A00F6u, dp4a_us(bot, 0x000300FDu, 0)));
-  gy = dp4a_us(bot, 0x00030A03u, dp4a_us(top, 0x00FDF6FDu, 0));
+  gx = dp4a_us(top, sw.d, dp4a_us(mid, sw.dm, dp4a_us(bot, sw.d, 0)));
+  gy = dp4a_us(bot, sw.sp, dp4a_us(top, sw.sm, 0));
 }
 
 // Writes the reflected border pixels (x = -1 -> 1, x = w -> w-2, then y = -1 -> 1, y = h -> h-2)
@@ -261,7 +262,8 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
 template <bool kDepth>
 __global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
-                    const int* __restrict__ slots, int n_slots, int item_begin, int item_count) {
+                    const int* __restrict__ slots, int n_slots, int item_begin, int item_count,
+                    const StencilWeights sw) {
   __shared__ __align__(16) uint8_t sg[2][kSegRows * kTilePitch8];
   __shared__ __align__(16) uint8_t si[2][kImgTileRows * kImgTilePitch];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -333,7 +335,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
             // a record carries (x, y) itself: the plain (x, y) list is kept only for the levels
             // EstimatePose never optimises (read-back of candidatePoints_ decodes either form)
             int gx, gy, i1;
-            scharr_from_tile(ti, x0, y0, x, y, gx, gy, i1);
+            scharr_from_tile(ti, x0, y0, x, y, sw, gx, gy, i1);
             rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
           } else {
             xy[o] = (uint32_t)x | ((uint32_t)y << 16);
@@ -376,11 +378,11 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   cand_scan_kernel<<<dim3(lr.lvl_count, n), 1024, 0, st>>>(g, p, d_slots, lr.lvl_begin);
   if (cudaGetLastError() != cudaSuccess) return -1;
   if (depth)
-    cand_scatter_kernel<true><<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
-                                                            lr.item_count);
+    cand_scatter_kernel<true><<<grid_scatter, 256, 0, st>>>(
+        g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op));
   else
-    cand_scatter_kernel<false><<<grid_scatter, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
-                                                             lr.item_count);
+    cand_scatter_kernel<false><<<grid_scatter, 256, 0, st>>>(
+        g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op));
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 3;
 }

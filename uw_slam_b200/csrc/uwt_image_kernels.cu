@@ -274,11 +274,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
   return d;
 }
-// Scharr rows as packed signed bytes over a 4-byte window (left, centre, right, unused)
-constexpr uint32_t kW_m3_0_3 = 0x000300FDu;     // (-3, 0, 3, 0)
-constexpr uint32_t kW_m10_0_10 = 0x000A00F6u;   // (-10, 0, 10, 0)
-constexpr uint32_t kW_3_10_3 = 0x00030A03u;     // (3, 10, 3, 0)
-constexpr uint32_t kW_m3_m10_m3 = 0x00FDF6FDu;  // (-3, -10, -3, 0)
 
 // The four 3-pixel windows of a 4-pixel group: window i = bytes [sx-1+i, sx+2+i] of the row.
 struct RowWin {
@@ -296,11 +291,15 @@ __device__ __forceinline__ RowWin row_windows(const uint8_t* srow, int sx) {
   return o;
 }
 
-template <bool kPlanes>
+template <bool kPlanes, bool kSobel>
 __global__ void __launch_bounds__(256)
 gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
                 const int* __restrict__ slots, int tile_begin, int16_t* __restrict__ gx_out,
                 int16_t* __restrict__ gy_out) {
+  // compile-time stencil rows: Scharr (reference) or Sobel (north-star option)
+  constexpr StencilWeights sw = kSobel
+                                    ? StencilWeights{0x000100FFu, 0x000200FEu, 0x00010201u, 0x00FFFEFFu}
+                                    : StencilWeights{0x000300FDu, 0x000A00F6u, 0x00030A03u, 0x00FDF6FDu};
   __shared__ __align__(128) uint8_t tile[kTileRows][kTileRowBytes];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t warp_sums[8];
@@ -389,9 +388,8 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         // Tracker.cpp:1133-1134: Scharr x / y, CV_16S
-        vx[i] = dp4a_us(top.w[i], kW_m3_0_3,
-                        dp4a_us(mid.w[i], kW_m10_0_10, dp4a_us(bot.w[i], kW_m3_0_3, 0)));
-        vy[i] = dp4a_us(bot.w[i], kW_3_10_3, dp4a_us(top.w[i], kW_m3_m10_m3, 0));
+        vx[i] = dp4a_us(top.w[i], sw.d, dp4a_us(mid.w[i], sw.dm, dp4a_us(bot.w[i], sw.d, 0)));
+        vy[i] = dp4a_us(bot.w[i], sw.sp, dp4a_us(top.w[i], sw.sm, 0));
         // Tracker.cpp:1139-1140: convertScaleAbs -> min(|v|, 255), packed 4 x u8
         ax |= (uint32_t)min(abs(vx[i]), 255) << (8 * i);
         ay |= (uint32_t)min(abs(vy[i]), 255) << (8 * i);
@@ -465,10 +463,17 @@ gradient_kernel(const __grid_constant__ Geom geom, const Pools pools,
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
                     const LevelRange& lr, int16_t* gx_out, int16_t* gy_out) {
   dim3 grid(lr.tile_count, n);
-  if (gx_out && gy_out)
-    gradient_kernel<true><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, gx_out, gy_out);
-  else
-    gradient_kernel<false><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, nullptr, nullptr);
+  const bool sobel = g.gradient_op == UWT_GRADIENT_SOBEL;
+  if (gx_out && gy_out) {  // read-back of the int16 planes (not on the hot path)
+    if (sobel)
+      gradient_kernel<true, true><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, gx_out, gy_out);
+    else
+      gradient_kernel<true, false><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, gx_out, gy_out);
+  } else if (sobel) {
+    gradient_kernel<false, true><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, nullptr, nullptr);
+  } else {
+    gradient_kernel<false, false><<<grid, 256, 0, st>>>(g, p, d_slots, lr.tile_begin, nullptr, nullptr);
+  }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -56,6 +56,8 @@ struct Geom {
   int weight_mode;    // UWT_WEIGHT_*
   float huber_delta;
   int depth_mode;     // UWT_DEPTH_*
+  int gradient_op;    // UWT_GRADIENT_*
+  int sampling;       // UWT_SAMPLE_*
   // per-slot strides (elements)
   size_t plane_elems, cand_elems, rec_elems, cnt_elems, tile_elems;
   int grad_tiles_total;  // gradient tiles per slot over all levels
@@ -76,6 +78,19 @@ struct Pools {
   uint16_t* dep;        // [slot][plane_elems]  16-bit depth pyramid (depth modes only)
   uint16_t* recz;       // [slot][rec_elems]    integer depth of every record (depth modes only)
 };
+
+// 3x3 derivative stencil as four packed signed-byte rows over a (left, centre, right, unused)
+// window: d = horizontal difference row (outer rows), dm = its middle row, sp / sm = +/- smoothing
+// row of the vertical difference.  Scharr (3, 10, 3) is the reference (Tracker.cpp:1133-1134),
+// Sobel (1, 2, 1) the north-star wording.
+struct StencilWeights {
+  uint32_t d, dm, sp, sm;
+};
+__host__ __device__ inline StencilWeights stencil_weights(int gradient_op) {
+  if (gradient_op == UWT_GRADIENT_SOBEL)
+    return {0x000100FFu, 0x000200FEu, 0x00010201u, 0x00FFFEFFu};
+  return {0x000300FDu, 0x000A00F6u, 0x00030A03u, 0x00FDF6FDu};
+}
 
 // The integer depth ObtainCandidatePoints reads for pixel (x, y) of a level (Tracker.cpp:1339,
 // 1344).  REFERENCE mode reproduces depths_[lvl].at<uchar>(y, x) on the CV_16U image: byte x of
