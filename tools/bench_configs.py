@@ -5,6 +5,7 @@
                          keyframe (re-keyed every 8 frames): single-problem latency
   --workload batch8192   config 3: 8192 independent 640x480 pairs, block-partitioned over the
                          ranks (strong scaling, no comms), processed in resident chunks
+  --workload hypotheses  config 3, hypothesis variant: one 640x480 pair, 8192 initial poses
   --workload shard4k     config 4: one 3840x2160 pair, GN loop sharded over the ranks with one
                          NCCL all-reduce of the 32 normal-equation sums per sweep
 
@@ -169,6 +170,53 @@ def batch8192(args, torch, dist, rank, local_rank, world):
     return res
 
 
+def hypotheses(args, torch, dist, rank, local_rank, world):
+    """Config 3, hypothesis variant: ONE 640x480 pair, `--pairs` initial-pose hypotheses split
+    over the ranks (strong scaling, no comms).  Every hypothesis is an independent problem that
+    shares the frame slots (prev = slot 0, cur = slot 1)."""
+    from oracle import uw_oracle as O
+    total, calib = args.pairs, "tum"
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    mine = hi - lo
+    chunk = min(args.chunk, mine)
+    t = make_tracker(calib, local_rank, max_frames=max(2, chunk), flags=args.flags)
+    prev, cur, _, _ = synth.render_pair(calib, 5)
+    t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.ApplyGradient([0])
+    t.ObtainCandidatePoints([0])
+    rng = np.random.default_rng(1234)
+    tang = (rng.normal(size=(total, 6)) * 2e-3).astype(np.float32)
+    init = np.stack([O.se3_exp(a) for a in tang[lo:hi]])
+    out = np.empty((mine, 7), np.float32)
+
+    def run():
+        for a in range(0, mine, chunk):
+            n = min(chunk, mine - a)
+            out[a:a + n] = t.EstimatePose([0] * n, [1] * n, init_poses=init[a:a + n])
+
+    run()
+    t.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    run()
+    t.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64,
+                      device=torch.device("cuda", local_rank))
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    res = {"metric": "pose estimates/sec, one 640x480 pair, %d initial-pose hypotheses" % total,
+           "value": total / float(dt.item()), "unit": "estimates/s", "hypotheses": total,
+           "n_gpus": world, "scaling": "strong", "chunk": chunk}
+    if rank == 0:
+        p = O.default_params(*synth.CALIB[calib])
+        rp, rc = O.FrameData(prev), O.FrameData(cur, with_candidates=False)
+        res["spot_check_bit_identical_to_oracle"] = all(
+            bool(np.array_equal(O.estimate_pose(p, rp, rc, init_pose=init[i])[0], out[i]))
+            for i in (0, mine // 2, mine - 1))
+    return res
+
+
 def shard4k(args, torch, dist, rank, local_rank, world):
     from uw_slam_b200.sharded import TrackerShardBackend, estimate_pose_sharded
     calib = "uhd"
@@ -225,7 +273,7 @@ def shard4k(args, torch, dist, rank, local_rank, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["euroc_seq", "batch8192", "shard4k"])
+    ap.add_argument("--workload", required=True, choices=["euroc_seq", "batch8192", "hypotheses", "shard4k"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--pairs", type=int, default=8192)
     ap.add_argument("--chunk", type=int, default=1024)
@@ -245,7 +293,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    res = {"euroc_seq": euroc_seq, "batch8192": batch8192, "shard4k": shard4k}[args.workload](
+    res = {"euroc_seq": euroc_seq, "batch8192": batch8192, "hypotheses": hypotheses,
+           "shard4k": shard4k}[args.workload](
         args, torch, dist, rank, local_rank, world)
     res["workload"] = args.workload
     if rank == 0:
