@@ -124,6 +124,7 @@ def test_rejected_configurations():
                 dict(first_level=1, last_level=2), dict(max_iterations=0), dict(max_frames=0),
                 dict(solve_mode=3), dict(solve_mode=2, lm_lambda=-1.0), dict(cluster_size=3),
                 dict(gradient_op=2), dict(sampling=2), dict(sampling=1, weight_mode=1),
+                dict(gradient_threshold=-1.0),
                 dict(device=99)):
         cfg = dict(bad)
         w, h = cfg.pop("width", 640), cfg.pop("height", 480)

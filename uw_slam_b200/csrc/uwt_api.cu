@@ -179,7 +179,7 @@ int build_geom(const uwt_config& c, Geom& g) {
   g.depth_mode = c.depth_mode;
   g.gradient_op = c.gradient_op;
   g.sampling = c.sampling;
-  size_t plane = 0, cand = 0, rec = 0, cnt = 0;
+  size_t plane = 0, mask = 0, rec = 0, cnt = 0;
   int tiles = 0, items = 0;
   // Tracker::InitializePyramid, Tracker.cpp:297-340 (same expression types as the source:
   // float members, double literals)
@@ -201,13 +201,16 @@ int build_geom(const uwt_config& c, Geom& g) {
     L.invfy = 1 / fy[l];
     L.plane_off = (int)plane;
     plane += align_up((size_t)L.pitch * L.h, 256);
-    L.cand_off = (int)cand;
-    cand += align_up((size_t)L.w * L.h, 64);
+    L.mask_wpr = (L.w + 31) / 32;
     if (l >= c.last_level && l <= c.first_level) {
       L.rec_off = (int)rec;
       rec += align_up((size_t)L.w * L.h, 64);
+      L.mask_off = -1;
     } else {
+      // a level EstimatePose never optimises keeps its selection as a bitmask
       L.rec_off = -1;
+      L.mask_off = (int)mask;
+      mask += align_up((size_t)L.mask_wpr * L.h, 64);
     }
     L.nstrip = (L.w + kStripW - 1) / kStripW;
     L.nseg = (L.h + kSegRows - 1) / kSegRows;
@@ -220,7 +223,8 @@ int build_geom(const uwt_config& c, Geom& g) {
     items += L.nstrip * L.nseg;
   }
   g.plane_elems = plane;
-  g.cand_elems = cand;
+  g.mask_elems = mask ? mask : 64;
+  g.mask_words_total = (int)mask;
   g.rec_elems = rec ? rec : 64;
   g.cnt_elems = cnt;
   g.tile_elems = align_up((size_t)tiles, 64);
@@ -273,7 +277,7 @@ void destroy_impl(uwt_tracker* t) {
   Pools& p = t->pools;
   cudaFree(p.img); cudaFree(p.g); cudaFree(p.gpart);
   cudaFree(p.ticket); cudaFree(p.ithr); cudaFree(p.cnt); cudaFree(p.ncand);
-  cudaFree(p.cand_xy); cudaFree(p.rec); cudaFree(p.dep); cudaFree(p.recz);
+  cudaFree(p.sel_mask); cudaFree(p.rec); cudaFree(p.dep); cudaFree(p.recz);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   for (ArgRegion& r : t->ring) {
     if (r.h_int) cudaFreeHost(r.h_int);
@@ -368,6 +372,8 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   if (c.first_level >= c.levels || c.last_level < 0 || c.last_level > c.first_level)
     return fail(nullptr, UWT_E_INVALID, "bad level range first=%d last=%d", c.first_level,
                 c.last_level);
+  if (!(c.gradient_threshold >= 0.0))
+    return fail(nullptr, UWT_E_INVALID, "gradient_threshold must be >= 0 (the reference uses 20)");
   if (c.max_iterations < 1 || c.max_frames < 1)
     return fail(nullptr, UWT_E_INVALID, "max_iterations and max_frames must be >= 1");
   if (c.solve_mode == UWT_SOLVE_CHOLESKY_LM && !(c.lm_lambda >= 0.0f))
@@ -435,7 +441,7 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   CREATE_CUDA(cudaMalloc(&p.ithr, F * kMaxLevels * sizeof(int)));
   CREATE_CUDA(cudaMalloc(&p.cnt, F * g.cnt_elems * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.ncand, F * kMaxLevels * sizeof(uint32_t)));
-  CREATE_CUDA(cudaMalloc(&p.cand_xy, F * g.cand_elems * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.sel_mask, F * g.mask_elems * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.rec, F * g.rec_elems * sizeof(uint64_t)));
   if (c.depth_mode != UWT_DEPTH_NONE) {
     CREATE_CUDA(cudaMalloc(&p.dep, F * g.plane_elems * sizeof(uint16_t)));
@@ -789,7 +795,7 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
   const bool lazy = (t->cfg.flags & UWT_FLAG_LAZY_LEVELS) != 0;
   const LevelRange lr = lazy ? level_range(t->geom, t->cfg.last_level, t->cfg.first_level)
                              : level_range(t->geom, 0, t->geom.levels - 1);
-  const int k = launch_candidates(t->geom, t->pools, n, r->d_int, t->stream, lr);
+  const int k = launch_candidates(t->geom, t->pools, n, r->d_int, t->stream, lr, !lazy);
   span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "candidate kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
@@ -1196,7 +1202,7 @@ static int complete_levels(uwt_tracker* t, int slot, int level, bool need_candid
     s.gradient_all = true;
   }
   if (do_cand) {
-    k = launch_candidates(t->geom, t->pools, 1, r->d_int, t->stream, all);
+    k = launch_candidates(t->geom, t->pools, 1, r->d_int, t->stream, all, true);
     if (k < 0) return fail(t, UWT_E_CUDA, "candidate kernel launch failed");
     t->launches += k;
     s.candidates_all = true;
@@ -1324,17 +1330,24 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
     }
     return UWT_OK;
   }
-  std::vector<uint32_t> xy(cnt);
-  UWT_CUDA(t, cudaMemcpyAsync(xy.data(),
-                              t->pools.cand_xy + (size_t)slot * t->geom.cand_elems + L.cand_off,
-                              sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, t->stream));
+  // a level without records: expand the selection bitmask in the reference's order, x outer and
+  // y inner (Tracker.cpp:1334-1335)
+  std::vector<uint32_t> mask((size_t)L.mask_wpr * L.h);
+  UWT_CUDA(t, cudaMemcpyAsync(mask.data(),
+                              t->pools.sel_mask + (size_t)slot * t->geom.mask_elems + L.mask_off,
+                              sizeof(uint32_t) * mask.size(), cudaMemcpyDeviceToHost, t->stream));
   UWT_CUDA(t, cudaStreamSynchronize(t->stream));
-  for (int i = 0; i < cnt; ++i) {  // candidatePoints_ rows, Tracker.cpp:1351-1355
-    pts4[i * 4 + 0] = (float)(xy[i] & 0xFFFFu);
-    pts4[i * 4 + 1] = (float)(xy[i] >> 16);
-    pts4[i * 4 + 2] = z_of((int)(xy[i] & 0xFFFFu), (int)(xy[i] >> 16));
-    pts4[i * 4 + 3] = 1.0f;
-  }
+  int i = 0;
+  for (int x = 0; x < L.w && i < cnt; ++x)
+    for (int y = 0; y < L.h && i < cnt; ++y)
+      if ((mask[(size_t)y * L.mask_wpr + (x >> 5)] >> (x & 31)) & 1u) {
+        pts4[i * 4 + 0] = (float)x;  // candidatePoints_ rows, Tracker.cpp:1351-1355
+        pts4[i * 4 + 1] = (float)y;
+        pts4[i * 4 + 2] = z_of(x, y);
+        pts4[i * 4 + 3] = 1.0f;
+        ++i;
+      }
+  if (i != cnt) return fail(t, UWT_E_CUDA, "selection bitmask holds %d points, count says %d", i, cnt);
   return UWT_OK;
 }
 

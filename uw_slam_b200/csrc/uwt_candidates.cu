@@ -224,6 +224,11 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
   const int lvl = blockIdx.x + lvl_begin;
   const int slot = slots[blockIdx.y];
   const LevelGeom& L = geom.lv[lvl];
+  if (L.rec_off < 0) {
+    // a level EstimatePose never optimises: cand_mask_kernel counts it with atomics, start at 0
+    if (threadIdx.x == 0) pools.ncand[(size_t)slot * kMaxLevels + lvl] = 0u;
+    return;
+  }
   const int M = L.w * L.nseg;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
@@ -300,7 +305,6 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
     const uint8_t* ti = si[buf];
     if (has_rec) patch_img_tile_borders(si[buf], L, x0, y0, t);
     const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
-    uint32_t* xy = pools.cand_xy + (size_t)slot * geom.cand_elems + L.cand_off;
     uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
     constexpr bool use_depth = kDepth;
     const uint16_t* dplane = kDepth ? pools.dep + (size_t)slot * geom.plane_elems + L.plane_off
@@ -331,15 +335,11 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
         if (sel) {
           const uint32_t o = base + __popc(b & lt_mask);
           if (has_rec && use_depth) recz[o] = (uint16_t)dz;
-          if (has_rec) {
-            // a record carries (x, y) itself: the plain (x, y) list is kept only for the levels
-            // EstimatePose never optimises (read-back of candidatePoints_ decodes either form)
-            int gx, gy, i1;
-            scharr_from_tile(ti, x0, y0, x, y, sw, gx, gy, i1);
-            rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
-          } else {
-            xy[o] = (uint32_t)x | ((uint32_t)y << 16);
-          }
+          // a record carries (x, y) itself; levels without records never reach this kernel
+          // (cand_mask_kernel keeps their selection as a bitmask)
+          int gx, gy, i1;
+          scharr_from_tile(ti, x0, y0, x, y, sw, gx, gy, i1);
+          rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
         }
         base += __popc(b);
       }
@@ -348,8 +348,84 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
   }
 }
 
+// Levels EstimatePose never optimises (level 0 by default: 75 % of all pixels; Tracker.cpp:389 only
+// walks first_level..last_level): ObtainCandidatePoints' selection is kept as a BITMASK plus the
+// count N_l.  Same threshold, same selected set; the x-major N x 4 list of candidatePoints_[l] is
+// expanded from the mask when an accessor asks for it (uwt_get_candidates), exactly like the float
+// matrix of the optimised levels is expanded from the packed records.  One thread = one mask
+// word = 32 pixels: two 16-byte loads, eight SWAR compares, a multiply that gathers the four 0/1
+// bytes of a compare into a nibble.
+template <bool kDepth>
+__global__ void __launch_bounds__(256)
+cand_mask_kernel(const __grid_constant__ Geom geom, const Pools pools,
+                 const int* __restrict__ slots, int lvl_lo, int lvl_hi) {
+  __shared__ uint32_t wsum[8];
+  const int slot = slots[blockIdx.y];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  // a CTA stays inside one level: per-level CTA ranges are computed from the level sizes
+  int lvl = -1, first_word = 0;
+  {
+    int cta = blockIdx.x;
+    for (int l = lvl_lo; l <= lvl_hi; ++l) {
+      if (geom.lv[l].rec_off >= 0) continue;
+      const int ctas = (geom.lv[l].mask_wpr * geom.lv[l].h + 255) / 256;
+      if (cta < ctas) {
+        lvl = l;
+        first_word = cta * 256;
+        break;
+      }
+      cta -= ctas;
+    }
+  }
+  if (lvl < 0) return;
+  const LevelGeom& L = geom.lv[lvl];
+  const int idx = first_word + t;
+  uint32_t word = 0;
+  if (idx < L.mask_wpr * L.h) {
+    const int row = idx / L.mask_wpr, x0 = (idx % L.mask_wpr) * 32;
+    const int ithr = pools.ithr[(size_t)slot * kMaxLevels + lvl];
+    if (ithr < 255) {
+      const uint32_t thr4 = (uint32_t)ithr * 0x01010101u;
+      const uint8_t* grow = pools.g + (size_t)slot * geom.plane_elems + L.plane_off +
+                            (size_t)row * L.pitch + x0;
+      uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+      // the pitch is a multiple of 16 and its padding is zero: 16-byte groups are all-or-nothing
+      if (x0 < L.pitch) a = __ldg(reinterpret_cast<const uint4*>(grow));
+      if (x0 + 16 < L.pitch) b = __ldg(reinterpret_cast<const uint4*>(grow + 16));
+      const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t m = __vsetgtu4(w8[j], thr4);           // 0 / 1 per byte
+        word |= ((m * 0x01020408u) >> 24) << (4 * j);          // -> 4 bits
+      }
+      if constexpr (kDepth) {  // Tracker.cpp:1339: depth != 0 as well
+        const uint16_t* dplane = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off;
+        uint32_t rest = word;
+        while (rest) {
+          const int bit = __ffs(rest) - 1;
+          rest &= rest - 1;
+          if (depth_at(dplane, L.pitch, x0 + bit, row, geom.depth_mode) == 0) word &= ~(1u << bit);
+        }
+      }
+    }
+    pools.sel_mask[(size_t)slot * geom.mask_elems + L.mask_off + idx] = word;
+  }
+  const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(word));
+  if (lane == 0) wsum[wid] = c;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += wsum[i];
+    if (s) atomicAdd(&pools.ncand[(size_t)slot * kMaxLevels + lvl], s);  // integer: order-free
+  }
+}
+
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
-                      const LevelRange& lr) {
+                      const LevelRange& lr_all, bool with_mask_levels) {
+  // Ordered stream compaction (count -> scan -> scatter) runs on the levels EstimatePose
+  // optimises; the other levels of the requested range keep a selection bitmask + count.
+  const LevelRange lr = level_range(g, g.last_level, g.first_level);
   // persistent grids: a multiple of the 148 SMs, as many CTAs per SM as the double-buffered
   // tiles allow; small jobs get one CTA per work item
   const long long total = (long long)lr.item_count * n;
@@ -368,6 +444,7 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   const int grid_count = (int)std::min<long long>(total, (long long)sms * per_sm_count);
   const int grid_scatter = (int)std::min<long long>(total, (long long)sms * per_sm_scatter);
   const bool depth = g.depth_mode != UWT_DEPTH_NONE;
+  int launches = 0;
   if (depth)
     cand_count_kernel<true><<<grid_count, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
                                                         lr.item_count);
@@ -375,8 +452,12 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
     cand_count_kernel<false><<<grid_count, 256, 0, st>>>(g, p, d_slots, n, lr.item_begin,
                                                          lr.item_count);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  cand_scan_kernel<<<dim3(lr.lvl_count, n), 1024, 0, st>>>(g, p, d_slots, lr.lvl_begin);
+  ++launches;
+  // scan: one CTA per (slot, level); on a bitmask level it only resets the count
+  const LevelRange& sr = with_mask_levels ? lr_all : lr;
+  cand_scan_kernel<<<dim3(sr.lvl_count, n), 1024, 0, st>>>(g, p, d_slots, sr.lvl_begin);
   if (cudaGetLastError() != cudaSuccess) return -1;
+  ++launches;
   if (depth)
     cand_scatter_kernel<true><<<grid_scatter, 256, 0, st>>>(
         g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op));
@@ -384,7 +465,22 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
     cand_scatter_kernel<false><<<grid_scatter, 256, 0, st>>>(
         g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op));
   if (cudaGetLastError() != cudaSuccess) return -1;
-  return 3;
+  ++launches;
+  if (with_mask_levels) {
+    const int lo = lr_all.lvl_begin, hi = lr_all.lvl_begin + lr_all.lvl_count - 1;
+    int ctas = 0;
+    for (int l = lo; l <= hi; ++l)
+      if (g.lv[l].rec_off < 0) ctas += (g.lv[l].mask_wpr * g.lv[l].h + 255) / 256;
+    if (ctas > 0) {
+      if (depth)
+        cand_mask_kernel<true><<<dim3(ctas, n), 256, 0, st>>>(g, p, d_slots, lo, hi);
+      else
+        cand_mask_kernel<false><<<dim3(ctas, n), 256, 0, st>>>(g, p, d_slots, lo, hi);
+      if (cudaGetLastError() != cudaSuccess) return -1;
+      ++launches;
+    }
+  }
+  return launches;
 }
 
 }  // namespace uwt

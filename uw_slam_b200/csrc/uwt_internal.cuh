@@ -37,7 +37,8 @@ __host__ __device__ inline uint64_t pack_record(uint32_t x, uint32_t y, uint32_t
 struct LevelGeom {
   int w, h, pitch;     // pitch in elements, multiple of 16
   int plane_off;       // element offset of this level inside a slot's image/gradient planes
-  int cand_off;        // element offset inside a slot's candidate (x,y) list
+  int mask_off;        // word offset of this level's selection bitmask, -1 if it has records
+  int mask_wpr;        // 32-bit words per bitmask row = ceil(w / 32)
   int rec_off;         // element offset inside a slot's record list, -1 if not optimised
   int nstrip, nseg;    // compaction decomposition
   int cnt_off;         // offset inside a slot's per-(column,segment) count array
@@ -59,7 +60,8 @@ struct Geom {
   int gradient_op;    // UWT_GRADIENT_*
   int sampling;       // UWT_SAMPLE_*
   // per-slot strides (elements)
-  size_t plane_elems, cand_elems, rec_elems, cnt_elems, tile_elems;
+  size_t plane_elems, mask_elems, rec_elems, cnt_elems, tile_elems;
+  int mask_words_total;  // bitmask words per slot over the levels without records
   int grad_tiles_total;  // gradient tiles per slot over all levels
   int warp_items_total;  // compaction tiles per slot over all levels
 };
@@ -73,7 +75,7 @@ struct Pools {
   int* ithr;            // [slot][kMaxLevels]   integer threshold per level
   uint32_t* cnt;        // [slot][cnt_elems]    counts, then exclusive offsets
   uint32_t* ncand;      // [slot][kMaxLevels]
-  uint32_t* cand_xy;    // [slot][cand_elems]   x | y << 16, reference (x-major) order
+  uint32_t* sel_mask;   // [slot][mask_elems]   selection bitmask of the levels without records
   uint64_t* rec;        // [slot][rec_elems]    packed records, same order
   uint16_t* dep;        // [slot][plane_elems]  16-bit depth pyramid (depth modes only)
   uint16_t* recz;       // [slot][rec_elems]    integer depth of every record (depth modes only)
@@ -190,7 +192,7 @@ int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, co
 int launch_gradient(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
                     const LevelRange& lr, int16_t* gx_out = nullptr, int16_t* gy_out = nullptr);
 int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, cudaStream_t st,
-                      const LevelRange& lr);
+                      const LevelRange& lr, bool with_mask_levels);
 constexpr int UWT_EST_MMA = 0;        // Gram accumulator in fp64 tensor-core fragments
 constexpr int UWT_EST_REGISTERS = 1;  // 27 fp64 register accumulators per thread
 int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, int cluster,
