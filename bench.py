@@ -433,7 +433,7 @@ def run_ours(args):
                                                                  2 * B * 21e6 / 1e9),
                        "cluster_size": args.cluster,
                        "estimate_kernel": ("cluster" if (args.cluster_kernel or args.cluster or
-                                                         args.weights or args.dmma_accum)
+                                                         args.dmma_accum)
                                            else "dataflow"),
                        "weights": ["identity", "tukey_mad", "huber"][args.weights],
                        "lazy_levels": bool(args.lazy_levels),
@@ -445,8 +445,8 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": ("estimate_kernel (cluster)"
-                                    if (args.cluster_kernel or args.cluster or args.weights or
-                                        args.dmma_accum) else "estimate_flow_kernel"),
+                                    if (args.cluster_kernel or args.cluster or args.dmma_accum)
+                                    else "estimate_flow_kernel"),
                          "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(B),

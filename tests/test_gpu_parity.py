@@ -278,6 +278,44 @@ def test_dataflow_kernel_traces_match_oracle(oracle, pairs):
     t.close()
 
 
+@pytest.mark.parametrize("calib,B", [("small", 36), ("tum", 24)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_dataflow_kernel_robust_weights_match_oracle(oracle, pairs, mode, calib, B):
+    """Robust weights on the dataflow kernel (>= 24 problems): Huber uses one table per CTA; a
+    Tukey sweep is a histogram round and an accumulation round of chunk tasks.  Every per-sweep
+    quantity must equal the oracle's, also for problems with no or few points and with an
+    occluder, and the cluster kernel must give the same bits."""
+    import uw_slam_b200._lib as L
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]   # "tum": several chunks per sweep on level 1
+    prevs = [pairs(calib, s % 6)[0] for s in range(B)]
+    curs = [pairs(calib, s % 6)[1].copy() for s in range(B)]
+    prevs[2] = np.full((h, w), 120, np.uint8)         # no candidates at all
+    curs[4] = prevs[4].copy()                         # identical frames: all residuals zero
+    curs[6][h // 4: h // 2, w // 4: w // 2] = 255     # occluder: the outliers Tukey rejects
+    prevs[9] = prevs[9].copy()
+    prevs[9][: h // 2] = 33
+    out = []
+    for flags in (L.FLAG_TRACE, L.FLAG_TRACE | L.FLAG_CLUSTER_KERNEL):
+        t = make_tracker(calib, max_frames=2 * B, flags=flags, weight_mode=mode, huber_delta=6.0)
+        fp = t.AddFrames(list(range(B)), np.stack(prevs))
+        fc = t.AddFrames(list(range(B, 2 * B)), np.stack(curs))
+        t.ApplyGradient(fp)
+        t.ObtainCandidatePoints(fp)
+        for rep in range(2):   # the histograms are re-armed per launch
+            poses, stats = t.EstimatePose(fp, fc, return_stats=True)
+        out.append((poses, [t.get_trace(s) for s in range(B)]))
+        t.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=6.0)
+    for s in range(B):
+        rp = oracle.FrameData(prevs[s])
+        rc = oracle.FrameData(curs[s], with_candidates=False)
+        opose, ostats, otrace = oracle.estimate_pose(p, rp, rc)
+        assert_trace_equal(out[0][1][s], otrace)
+        assert_trace_equal(out[1][1][s], otrace)
+        assert np.array_equal(out[0][0][s], opose), s
+
+
 def test_dataflow_and_cluster_kernels_agree_bitwise(pairs):
     import uw_slam_b200._lib as L
     calib = "tum_mono"
