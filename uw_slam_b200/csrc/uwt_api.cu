@@ -956,6 +956,9 @@ int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* s
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   // waits for the estimate + its D2H only, not for work enqueued after it
   UWT_CUDA(t, cudaEventSynchronize(t->poses_ready));
+#ifdef UWT_FLOW_STATS
+  if (t->flow_last) flow_debug_dump();
+#endif
   if (t->flow_last && (t->h_flow_ctl[3] != 0 || t->h_flow_ctl[2] != 0))
     return fail(t, UWT_E_CUDA, "dataflow estimate kernel did not complete (error %d, %d problems "
                 "unfinished)", t->h_flow_ctl[3], t->h_flow_ctl[2]);

@@ -199,6 +199,9 @@ int launch_estimate(const Geom& g, const Pools& p, int n, const EstimateIO& io, 
                     cudaStream_t st, int variant);
 // persistent dataflow form for batches (chunk tasks from a global ring, no barriers)
 size_t flow_workspace_bytes(const Geom& g, int nprob);
+#ifdef UWT_FLOW_STATS
+void flow_debug_dump();
+#endif
 int launch_estimate_flow(const Geom& g, const Pools& p, int n, const EstimateIO& io,
                          void* workspace, cudaStream_t st);
 int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, double* partials,
