@@ -24,9 +24,12 @@ constexpr int kRing = 8;
 // The dataflow estimate kernel serves the batch sizes where one-cluster-per-problem suffers from
 // wave quantisation and per-sweep barriers (measured on B200, 128 problems at 1280x1024: 0.96 vs
 // 1.03 ms).  Fewer problems: the 16-CTA cluster has the lower latency; from 2 CTAs per SM upwards
-// single-CTA problems balance by themselves (8192 x 640x480: 260 k vs 244 k tracks/s).
+// single-CTA problems balance by themselves (8192 x 640x480: 330 k vs 310 k tracks/s).
 constexpr int kFlowMinProblems = 24;
-constexpr int kFlowMaxProblems = 2 * 148;
+#ifndef UWT_FLOW_MAX_PROBLEMS
+#define UWT_FLOW_MAX_PROBLEMS (2 * 148)
+#endif
+constexpr int kFlowMaxProblems = UWT_FLOW_MAX_PROBLEMS;
 constexpr int kTraceProblems = 64;
 
 thread_local std::string g_create_error;
