@@ -74,6 +74,15 @@ extern "C" {
 #define UWT_DEPTH_REFERENCE 1 /* as shipped: depths_[lvl].at<uchar>(y,x) on the 16-bit image, i.e.
                                  BYTE x of row y (low / high byte of depth pixel x/2)             */
 #define UWT_DEPTH_U16 2       /* what the code evidently means: at<ushort>(y,x)                   */
+#define UWT_DEPTH_ALL_POINTS 3 /* Tracker::ObtainAllPoints (src/Tracker.cpp:1259-1310) in place of
+                                 ObtainCandidatePoints: EVERY pixel whose depth, read as
+                                 at<short>(y,x), is > 0 is a point, with Z = depth * (0.0002 /
+                                 2^level); no gradient threshold.  The reference appends a row
+                                 (0,0,1,0) for every other pixel: such a row warps to (0,0), fails
+                                 the strict bounds test of EstimatePose (src/Tracker.cpp:450) and
+                                 contributes nothing, so those rows are not materialised here
+                                 (n_points counts the points with depth); points are kept in the
+                                 x-major order of the other modes                                */
 
 /* Derivative stencil of Tracker::ApplyGradient (src/Tracker.cpp:1133-1134). */
 #define UWT_GRADIENT_SCHARR 0 /* cv::Scharr, the reference                                        */

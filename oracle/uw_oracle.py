@@ -15,7 +15,7 @@ MAX_LEVELS = 8
 SOLVE_LU, SOLVE_INVERSE, SOLVE_CHOLESKY_LM = 0, 1, 2
 ACCUM_DOUBLE, ACCUM_LONGDOUBLE = 0, 1
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
-DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16 = 0, 1, 2
+DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16, DEPTH_ALL_POINTS = 0, 1, 2, 3
 
 
 class Params(C.Structure):
@@ -362,8 +362,27 @@ def candidates_depth(g, depth, gradient_threshold=20.0, depth_mode=DEPTH_REFEREN
     return pts[:n].copy(), z[:n].copy()
 
 
+def all_points_depth(depth, lvl):
+    """Tracker::ObtainAllPoints, depth branch (Tracker.cpp:1259-1300): one row per pixel in
+    ROW-major order (:1268-1269); [x, y, at<short>(y,x) * (0.0002 / 2^lvl), 1] where the depth
+    read as a signed short is > 0 (:1273-1279), [0, 0, 1, 0] elsewhere (:1290-1292)."""
+    d = np.ascontiguousarray(depth, np.uint16).view(np.int16)
+    h, w = d.shape
+    factor_lvl = np.float32(np.float64(np.float32(0.0002)) / np.float64(2.0 ** lvl))  # :1266
+    pts = np.zeros((h * w, 4), np.float32)
+    pts[:, 2] = 1.0
+    ys, xs = np.divmod(np.arange(h * w), w)
+    v = d.ravel() > 0
+    pts[v, 0] = xs[v]
+    pts[v, 1] = ys[v]
+    pts[v, 2] = d.ravel()[v].astype(np.float32) * factor_lvl
+    pts[v, 3] = 1.0
+    return pts
+
+
 class FrameData:
-    """What uw::Frame holds after pyramid + ApplyGradient + ObtainCandidatePoints."""
+    """What uw::Frame holds after pyramid + ApplyGradient + ObtainCandidatePoints (or, with
+    depth_mode = DEPTH_ALL_POINTS, ObtainAllPoints)."""
 
     def __init__(self, img, levels=5, gradient_threshold=20.0, with_candidates=True, depth=None,
                  depth_mode=DEPTH_NONE, gradient_op=0):
@@ -379,7 +398,9 @@ class FrameData:
                 gx, gy = sobel(im) if gradient_op == 1 else scharr(im)
                 g = gradmag(gx, gy)
                 c, m, t = candidates(g, gradient_threshold)
-                if self.depths:
+                if self.depths and depth_mode == DEPTH_ALL_POINTS:
+                    c = all_points_depth(self.depths[lvl], lvl)
+                elif self.depths:
                     c, z = candidates_depth(g, self.depths[lvl], gradient_threshold, depth_mode)
                     self.zsrc.append(z)
                 self.gx.append(gx)

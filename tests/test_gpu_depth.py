@@ -76,6 +76,55 @@ def test_depth_tracking_matches_oracle(oracle, calib, seed, batch, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("calib,seed,batch", [("small", 4, 1), ("tum", 2, 1), ("small", 20, 6)])
+def test_all_points_tracking_matches_oracle(oracle, calib, seed, batch):
+    """Tracker::ObtainAllPoints (Tracker.cpp:1259-1310) + EstimatePose: every pixel whose depth,
+    read as a signed short, is > 0, with Z = depth * 0.0002 / 2^level and no gradient test.  The
+    oracle builds the reference's row-major list including its [0, 0, 1, 0] rows; the library
+    keeps the points with depth, x-major: same points, and every sweep must give the same bits."""
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    pairs = [synth.render_pair(calib, seed + i)[:2] for i in range(batch)]
+    deps = [make_depth((h, w), seed + i) for i in range(batch)]
+    for d in deps:
+        d[7::13, 5::9] = 0x8000 + 77      # negative as a short: not a point (Tracker.cpp:1273)
+    t = U.Tracker(True, depth_mode=L.DEPTH_ALL_POINTS)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=2 * batch, flags=L.FLAG_TRACE)
+    fp = t.AddFrames(list(range(batch)), np.stack([p[0] for p in pairs]))
+    fc = t.AddFrames(list(range(batch, 2 * batch)), np.stack([p[1] for p in pairs]))
+    t.ApplyGradient(fp)
+    t.AddDepthFrames([f.slot for f in fp], np.stack(deps))
+    t.ObtainAllPoints(fp)
+    poses, stats = t.EstimatePose(fp, fc, return_stats=True)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for i in range(batch):
+        rp = oracle.FrameData(pairs[i][0], depth=deps[i], depth_mode=oracle.DEPTH_ALL_POINTS)
+        rc = oracle.FrameData(pairs[i][1], with_candidates=False)
+        if i == 0:
+            for lvl in range(5):
+                ref = rp.cand[lvl]
+                assert ref.shape[0] == rp.images[lvl].size           # one row per pixel
+                ref = ref[ref[:, 3] == 1.0]                          # the rows that are points
+                got = fp[0].candidatePoints(lvl)                     # x-major
+                assert got.shape == ref.shape, (lvl, got.shape, ref.shape)
+                order = np.lexsort((ref[:, 1], ref[:, 0]))           # row-major -> x-major
+                assert np.array_equal(got, ref[order]), lvl
+                assert list(stats[0].n_points)[lvl] == ref.shape[0] or lvl == 0
+        opose, ostats, otrace = oracle.estimate_pose(p, rp, rc)
+        tr = t.get_trace(i)
+        assert [(a.level, a.k, a.n_valid, a.broke, a.sum_r2) for a in tr] == \
+            [(b.level, b.k, b.n_valid, b.broke, b.sum_r2) for b in otrace], i
+        for a, b in zip(tr, otrace):
+            assert np.array_equal(np.array(a.A[:]), np.array(b.A[:])), (i, b.level, b.k)
+            assert np.array_equal(np.array(a.delta[:]), np.array(b.delta[:])), (i, b.level, b.k)
+            assert np.array_equal(np.array(a.pose[:]), np.array(b.pose[:])), (i, b.level, b.k)
+        assert np.array_equal(poses[i], opose), i
+    t.close()
+
+
+@pytest.mark.gpu
 def test_depth_api_rules():
     import uw_slam_b200 as U
     import uw_slam_b200._lib as L
@@ -86,8 +135,8 @@ def test_depth_api_rules():
     with pytest.raises(U.UwtError):      # mono tracker takes no depth
         t.AddDepthFrames([0], np.ones((h, w), np.uint16))
     t.close()
-    for bad in (dict(depth_mode=3), dict(depth_mode=1, weight_mode=1),
-                dict(depth_mode=2, flags=L.FLAG_DMMA_ACCUM)):
+    for bad in (dict(depth_mode=4), dict(depth_mode=3, weight_mode=1),
+                dict(depth_mode=1, weight_mode=1), dict(depth_mode=2, flags=L.FLAG_DMMA_ACCUM)):
         with pytest.raises(U.UwtError):
             U.Tracker(False).InitializePyramid(w, h, K, **bad)
     # all-zero depth: no candidates anywhere, identity pose (ARITHMETIC.md U2)

@@ -397,7 +397,7 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
                 "bilinear sampling supports identity weights, mono input, register accumulator");
   if (c.gradient_op != UWT_GRADIENT_SCHARR && c.gradient_op != UWT_GRADIENT_SOBEL)
     return fail(nullptr, UWT_E_INVALID, "bad gradient_op %d", c.gradient_op);
-  if (c.depth_mode < UWT_DEPTH_NONE || c.depth_mode > UWT_DEPTH_U16)
+  if (c.depth_mode < UWT_DEPTH_NONE || c.depth_mode > UWT_DEPTH_ALL_POINTS)
     return fail(nullptr, UWT_E_INVALID, "bad depth_mode %d", c.depth_mode);
   if (c.depth_mode != UWT_DEPTH_NONE &&
       (c.weight_mode != UWT_WEIGHT_IDENTITY || (c.flags & UWT_FLAG_DMMA_ACCUM)))
@@ -1308,13 +1308,17 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
     rc = uwt_get_depth(t, slot, level, dplane.data());
     if (rc) return rc;
   }
-  const float factor = 0.0002;  // Tracker.cpp:1316
+  // Tracker.cpp:1316; ObtainAllPoints: factor / 2^level (Tracker.cpp:1266)
+  const float factor =
+      t->cfg.depth_mode == UWT_DEPTH_ALL_POINTS ? std::ldexp(0.0002f, -level) : 0.0002f;
   auto z_of = [&](int x, int y) -> float {
     if (dplane.empty()) return 1.0f;  // depth_initialization, Tracker.cpp:1317
     int d;
     if (t->cfg.depth_mode == UWT_DEPTH_REFERENCE) {
       const unsigned v = dplane[(size_t)y * L.w + (x >> 1)];
       d = (x & 1) ? (int)(v >> 8) : (int)(v & 0xFFu);
+    } else if (t->cfg.depth_mode == UWT_DEPTH_ALL_POINTS) {
+      d = (int)(int16_t)dplane[(size_t)y * L.w + x];
     } else {
       d = dplane[(size_t)y * L.w + x];
     }

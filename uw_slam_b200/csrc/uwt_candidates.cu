@@ -170,7 +170,9 @@ cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
     const uint8_t* plane = pools.g + (size_t)slot * geom.plane_elems + L.plane_off;
     const int gx = x0 + lane * 4;
     uint32_t acc = 0;
-    if (ithr < 255 && gx < L.pitch) {  // g <= 255: a threshold of 255 or more selects nothing
+    // ObtainAllPoints (UWT_DEPTH_ALL_POINTS): every pixel with depth, no gradient test
+    const bool all = kDepth && geom.depth_mode == UWT_DEPTH_ALL_POINTS;
+    if ((ithr < 255 || all) && gx < L.pitch) {  // g <= 255: a threshold >= 255 selects nothing
       const uint32_t thr4 = (uint32_t)ithr * 0x01010101u;
       uint32_t w[kRowsPerWarp];
 #pragma unroll
@@ -196,7 +198,7 @@ cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
               if (gx + i < L.w && depth_at(dplane, L.pitch, gx + i, gy, geom.depth_mode) != 0)
                 nz |= 1u << (8 * i);
           }
-          acc += __vsetgtu4(w[r], thr4) & nz;
+          acc += (all ? 0x01010101u : __vsetgtu4(w[r], thr4)) & nz;
         }
       }
     }
@@ -307,6 +309,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
     const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
     uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
     constexpr bool use_depth = kDepth;
+    const bool all_points = kDepth && geom.depth_mode == UWT_DEPTH_ALL_POINTS;
     const uint16_t* dplane = kDepth ? pools.dep + (size_t)slot * geom.plane_elems + L.plane_off
                                     : nullptr;
     uint16_t* recz =
@@ -325,7 +328,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
 #pragma unroll
       for (int ch = 0; ch < kSegRows / 32; ++ch) {
         const int row = ch * 32 + lane, y = y0 + row;
-        bool sel = (y < L.h) && ((uint32_t)tg[row * kTilePitch8 + c] > ithr);
+        bool sel = (y < L.h) && (all_points || (uint32_t)tg[row * kTilePitch8 + c] > ithr);
         int dz = 0;
         if (use_depth && sel) {  // Tracker.cpp:1339: depth != 0 as well
           dz = depth_at(dplane, L.pitch, x, y, geom.depth_mode);
@@ -384,7 +387,8 @@ cand_mask_kernel(const __grid_constant__ Geom geom, const Pools pools,
   if (idx < L.mask_wpr * L.h) {
     const int row = idx / L.mask_wpr, x0 = (idx % L.mask_wpr) * 32;
     const int ithr = pools.ithr[(size_t)slot * kMaxLevels + lvl];
-    if (ithr < 255) {
+    const bool all = kDepth && geom.depth_mode == UWT_DEPTH_ALL_POINTS;
+    if (ithr < 255 || all) {
       const uint32_t thr4 = (uint32_t)ithr * 0x01010101u;
       const uint8_t* grow = pools.g + (size_t)slot * geom.plane_elems + L.plane_off +
                             (size_t)row * L.pitch + x0;
@@ -395,7 +399,7 @@ cand_mask_kernel(const __grid_constant__ Geom geom, const Pools pools,
       const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t m = __vsetgtu4(w8[j], thr4);           // 0 / 1 per byte
+        const uint32_t m = all ? 0x01010101u : __vsetgtu4(w8[j], thr4);  // 0 / 1 per byte
         word |= ((m * 0x01020408u) >> 24) << (4 * j);          // -> 4 bits
       }
       if constexpr (kDepth) {  // Tracker.cpp:1339: depth != 0 as well
@@ -404,7 +408,8 @@ cand_mask_kernel(const __grid_constant__ Geom geom, const Pools pools,
         while (rest) {
           const int bit = __ffs(rest) - 1;
           rest &= rest - 1;
-          if (depth_at(dplane, L.pitch, x0 + bit, row, geom.depth_mode) == 0) word &= ~(1u << bit);
+          if (x0 + bit >= L.w || depth_at(dplane, L.pitch, x0 + bit, row, geom.depth_mode) == 0)
+            word &= ~(1u << bit);
         }
       }
     }

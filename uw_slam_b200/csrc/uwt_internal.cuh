@@ -103,6 +103,10 @@ __device__ __forceinline__ int depth_at(const uint16_t* __restrict__ plane, int 
     const unsigned v = plane[(size_t)y * pitch + (x >> 1)];
     return (x & 1) ? (int)(v >> 8) : (int)(v & 0xFFu);
   }
+  if (depth_mode == UWT_DEPTH_ALL_POINTS) {  // at<short>(y, x) > 0, Tracker.cpp:1273
+    const int v = (int)(int16_t)plane[(size_t)y * pitch + x];
+    return v > 0 ? v : 0;
+  }
   return (int)plane[(size_t)y * pitch + x];
 }
 

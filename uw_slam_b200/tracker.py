@@ -313,6 +313,13 @@ class Tracker:
         for f in self._as_frames(frames):
             f.obtained_candidatePoints_ = True
 
+    # -- Tracker::ObtainAllPoints(Frame*), Tracker.cpp:1259: every pixel with depth > 0 ------
+    def ObtainAllPoints(self, frames):
+        if self.cfg is None or self.cfg.depth_mode != L.DEPTH_ALL_POINTS:
+            raise UwtError(-1, "ObtainAllPoints needs a tracker created with "
+                               "depth_mode=DEPTH_ALL_POINTS")
+        self.ObtainCandidatePoints(frames)
+
     # -- Tracker::EstimatePose(Frame* prev, Frame* cur), Tracker.cpp:362 ---------------------
     def EstimatePose(self, prev, cur, init_poses=None, return_stats=False):
         pa, pp, n = self._slots(self._as_slots(prev))
