@@ -263,6 +263,14 @@ class Tracker {
     Check(uwt_select_candidates(h_, 1, &f->slot));
     f->obtained_candidatePoints_ = true;
   }
+  // include/Tracker.h:153 (src/Tracker.cpp:1259): every pixel with depth > 0 is a point.  The
+  // point rule is part of the tracker's configuration here: set
+  // config().depth_mode = UWT_DEPTH_ALL_POINTS before InitializePyramid.
+  void ObtainAllPoints(Frame* f) {
+    if (cfg_.depth_mode != UWT_DEPTH_ALL_POINTS)
+      throw std::runtime_error("ObtainAllPoints: config().depth_mode != UWT_DEPTH_ALL_POINTS");
+    ObtainCandidatePoints(f);
+  }
   // include/Tracker.h:122: writes prev->rigid_transformation_ (Tracker.cpp:595)
   void EstimatePose(Frame* prev, Frame* cur, uwt_track_stats* stats = nullptr) {
     Check(uwt_estimate_pose(h_, 1, &prev->slot, &cur->slot, nullptr,
