@@ -75,6 +75,46 @@ def test_depth_tracking_matches_oracle(oracle, calib, seed, batch, mode):
     t.close()
 
 
+def test_all_points_oracle_follows_the_reference_loops(oracle):
+    """oracle.all_points_depth against a literal restatement of Tracker.cpp:1264-1300, and the
+    property the library relies on: the [0, 0, 1, 0] rows never take part in a sweep, and the
+    order of the points does not change any rounded result."""
+    rng = np.random.default_rng(5)
+    h, w = 24, 40
+    d = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+    d[rng.random((h, w)) < 0.3] = 0
+    for lvl in (0, 2, 4):
+        factor_lvl = np.float32(np.float64(np.float32(0.0002)) / 2.0 ** lvl)   # :1266
+        rows = []
+        for y in range(h):               # Tracker.cpp:1268
+            for x in range(w):           # Tracker.cpp:1269
+                v = int(d[y, x]) - 65536 if d[y, x] >= 32768 else int(d[y, x])   # at<short>
+                if v > 0:
+                    rows.append([x, y, np.float32(v) * factor_lvl, 1.0])
+                else:
+                    rows.append([0.0, 0.0, 1.0, 0.0])
+        assert np.array_equal(oracle.all_points_depth(d, lvl), np.array(rows, np.float32))
+    calib = "small"
+    wd, hd, fx, fy, cx, cy = synth.CALIB[calib]
+    a, b = synth.render_pair(calib, 4)[:2]
+    dep = make_depth((hd, wd), 4)
+    dep[7::13, 5::9] = 0x8000 + 77
+    p = oracle.default_params(wd, hd, fx, fy, cx, cy)
+    rp = oracle.FrameData(a, depth=dep, depth_mode=oracle.DEPTH_ALL_POINTS)
+    rc = oracle.FrameData(b, with_candidates=False)
+    pose, st, tr = oracle.estimate_pose(p, rp, rc)
+    for lvl in range(5):                 # points only, x-major: what the library keeps
+        c = rp.cand[lvl]
+        c = c[c[:, 3] == 1.0]
+        rp.cand[lvl] = c[np.lexsort((c[:, 1], c[:, 0]))]
+    pose2, st2, tr2 = oracle.estimate_pose(p, rp, rc)
+    assert np.array_equal(pose, pose2) and len(tr) == len(tr2)
+    for x, y in zip(tr, tr2):
+        assert (x.level, x.k, x.n_valid, x.sum_r2) == (y.level, y.k, y.n_valid, y.sum_r2)
+        assert np.array_equal(np.array(x.A[:]), np.array(y.A[:]))
+        assert np.array_equal(np.array(x.b[:]), np.array(y.b[:]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("calib,seed,batch", [("small", 4, 1), ("tum", 2, 1), ("small", 20, 6)])
 def test_all_points_tracking_matches_oracle(oracle, calib, seed, batch):
