@@ -14,6 +14,8 @@
  *                                                               uwt_set_frames_device
  *   Tracker::ApplyGradient(Frame*)      include/Tracker.h:137   uwt_apply_gradient
  *   Tracker::ObtainCandidatePoints(F*)  include/Tracker.h:145   uwt_select_candidates
+ *   Tracker::ObtainAllPoints(Frame*)    include/Tracker.h:153   uwt_select_candidates with
+ *                                       src/Tracker.cpp:1259    cfg.depth_mode = UWT_DEPTH_ALL_POINTS
  *   Tracker::EstimatePose(F*,F*)        include/Tracker.h:122   uwt_estimate_pose
  *   Tracker::WarpFunction(Mat,SE3,int)  include/Tracker.h:193   uwt_warp_points
  *   CameraModel::GetCameraModel (rectify) src/CameraModel.cpp:84 uwt_camera_optimal_matrix,
