@@ -133,15 +133,17 @@ def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights
     ifx, ify = f32(K["invfx"][lvl]), f32(K["invfy"][lvl])
     rows, cols = I2.shape
     x1, y1 = pts[:, 0], pts[:, 1]
-    X = ((x1 - cx) * ifx).astype(f32)
-    Y = ((y1 - cy) * ify).astype(f32)
+    Z, W = pts[:, 2].astype(f32), pts[:, 3].astype(f32)   # mono: Z = W = 1 (every product exact)
+    X = (((x1 - cx) * ifx).astype(f32) * Z).astype(f32)   # Tracker.cpp:1439-1441
+    Y = (((y1 - cy) * ify).astype(f32) * Z).astype(f32)
     R = np_quat_to_R(pose[:4]).astype(np.float64)
     t = pose[4:].astype(np.float64)
-    Xd, Yd = X.astype(np.float64), Y.astype(np.float64)
-    o = [(R[r, 0] * Xd + (R[r, 1] * Yd + (R[r, 2] + t[r]))).astype(f32) for r in range(3)]
+    Xd, Yd, Zd, Wd = (v.astype(np.float64) for v in (X, Y, Z, W))
+    o = [(R[r, 0] * Xd + (R[r, 1] * Yd + (R[r, 2] * Zd + t[r] * Wd))).astype(f32)
+         for r in range(3)]
     with np.errstate(divide="ignore", invalid="ignore"):
-        x2 = ((o[0] * fx) / o[2] + cx).astype(f32)
-        y2 = ((o[1] * fy) / o[2] + cy).astype(f32)
+        x2 = (((o[0] * fx) / o[2] + cx).astype(f32) * W).astype(f32)   # Tracker.cpp:1460-1467
+        y2 = (((o[1] * fy) / o[2] + cy).astype(f32) * W).astype(f32)
     z2 = o[2]
     valid = (y2 > 0) & (y2 < f32(rows)) & (x2 > 0) & (x2 < f32(cols)) & (z2 != 0)
     x1, y1, x2, y2, z2 = x1[valid], y1[valid], x2[valid], y2[valid], z2[valid]
@@ -184,13 +186,20 @@ def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights
     return A, b, int(valid.sum()), int((r * r).sum())
 
 
-@pytest.mark.parametrize("calib,seed,mode", [("small", 0, 0), ("tum", 2, 0), ("small", 1, 1),
-                                             ("tum", 2, 1), ("small", 1, 2)])
-def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed, mode):
+@pytest.mark.parametrize("calib,seed,mode,depth_mode", [
+    ("small", 0, 0, 0), ("tum", 2, 0, 0), ("small", 1, 1, 0), ("tum", 2, 1, 0), ("small", 1, 2, 0),
+    ("small", 3, 0, 1), ("small", 3, 0, 2), ("small", 4, 0, 3), ("tum", 2, 0, 3)])
+def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed, mode, depth_mode):
     cv2 = pytest.importorskip("cv2")
     w, h, fx, fy, cx, cy = synth.CALIB[calib]
     prev, cur, _, _ = synth.render_pair(calib, seed)
-    fp, fc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
+    depth = None
+    if depth_mode:   # per-point depth (ARITHMETIC.md D2-D4): [x, y, Z, W] rows from the oracle
+        from test_gpu_depth import make_depth
+        depth = make_depth((h, w), seed)
+        depth[7::13, 5::9] = 0x8000 + 77
+    fp = oracle.FrameData(prev, depth=depth, depth_mode=depth_mode)
+    fc = oracle.FrameData(cur, with_candidates=False)
     p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=7.5)
     _, _, tr = oracle.estimate_pose(p, fp, fc)
     weight_fn = None
