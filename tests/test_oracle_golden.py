@@ -126,7 +126,8 @@ def np_quat_to_R(q):
                      [txz - twy, tyz + twx, one - (txx + tyy)]], f32)
 
 
-def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights=False):
+def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights=False,
+                 bilinear=False):
     """A, b (float32), n_valid, sum_r2 [, weighted error sum] for one sweep; vectorised float32
     numpy, sums by fsum.  weight_fn(residuals f32) -> weights f32 (Tracker.cpp:496)."""
     fx, fy, cx, cy = (f32(K[k][lvl]) for k in ("fx", "fy", "cx", "cy"))
@@ -168,6 +169,19 @@ def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights
         J[:, c] = (jx * a + jy * b).astype(f32).astype(np.float64)
     r50 = (r.astype(f32) * f32(50)).astype(np.float64)
     esum = None
+    if bilinear:   # ARITHMETIC.md B1: float interpolation of the four neighbours of (x2, y2)
+        ix, iy = x2.astype(np.int64), y2.astype(np.int64)
+        ax, ay = (x2 - ix.astype(f32)).astype(f32), (y2 - iy.astype(f32)).astype(f32)
+        ix1, iy1 = np.minimum(ix + 1, cols - 1), np.minimum(iy + 1, rows - 1)
+        a, b_ = I2[iy, ix].astype(f32), I2[iy, ix1].astype(f32)
+        c_, d = I2[iy1, ix].astype(f32), I2[iy1, ix1].astype(f32)
+        top = (a + (ax * (b_ - a)).astype(f32)).astype(f32)
+        bot = (c_ + (ax * (d - c_)).astype(f32)).astype(f32)
+        v = (top + (ay * (bot - top)).astype(f32)).astype(f32)
+        rf = (v - I1[ys, xs].astype(f32)).astype(f32)
+        r50 = (rf * f32(50)).astype(f32).astype(np.float64)
+        esum = math.fsum(rf.astype(np.float64) ** 2)
+        r = np.zeros_like(r)           # the integer side-sum is reported as 0
     if weight_fn is not None:
         rf = r.astype(f32)
         wgt = weight_fn(rf).astype(f32)
@@ -181,15 +195,18 @@ def np_iteration(pts, I1, I2, gx, gy, pose, K, lvl, weight_fn=None, sqrt_weights
         for j in range(i, 6):
             A[i, j] = A[j, i] = f32(math.fsum(J[:, i] * J[:, j]))   # exactly rounded sums
         b[i] = f32(-math.fsum(J[:, i] * r50))
-    if weight_fn is not None:
+    if weight_fn is not None or bilinear:
         return A, b, int(valid.sum()), int((r * r).sum()), esum
     return A, b, int(valid.sum()), int((r * r).sum())
 
 
 @pytest.mark.parametrize("calib,seed,mode,depth_mode", [
     ("small", 0, 0, 0), ("tum", 2, 0, 0), ("small", 1, 1, 0), ("tum", 2, 1, 0), ("small", 1, 2, 0),
-    ("small", 3, 0, 1), ("small", 3, 0, 2), ("small", 4, 0, 3), ("tum", 2, 0, 3)])
+    ("small", 3, 0, 1), ("small", 3, 0, 2), ("small", 4, 0, 3), ("tum", 2, 0, 3),
+    ("small", 2, 0, -1), ("tum", 3, 0, -1)])        # depth_mode -1: mono, bilinear sampling (B1)
 def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed, mode, depth_mode):
+    bilinear = depth_mode < 0
+    depth_mode = max(depth_mode, 0)
     cv2 = pytest.importorskip("cv2")
     w, h, fx, fy, cx, cy = synth.CALIB[calib]
     prev, cur, _, _ = synth.render_pair(calib, seed)
@@ -200,7 +217,8 @@ def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed, m
         depth[7::13, 5::9] = 0x8000 + 77
     fp = oracle.FrameData(prev, depth=depth, depth_mode=depth_mode)
     fc = oracle.FrameData(cur, with_candidates=False)
-    p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=7.5)
+    p = oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=mode, huber_delta=7.5,
+                              sampling=1 if bilinear else 0)
     _, _, tr = oracle.estimate_pose(p, fp, fc)
     weight_fn = None
     if mode == 1:   # Tukey / MAD evaluated with the real OpenCV (tests/test_oracle_vs_cv2.py)
@@ -219,10 +237,12 @@ def test_every_traced_iteration_matches_numpy_restatement(oracle, calib, seed, m
             pose = oracle.se3_scale_level(pose)
         lvl = t.level
         res = np_iteration(fp.cand[lvl], fp.images[lvl], fc.images[lvl], fp.gx[lvl],
-                           fp.gy[lvl], pose, K, lvl, weight_fn, sqrt_weights=(mode == 2))
+                           fp.gy[lvl], pose, K, lvl, weight_fn, sqrt_weights=(mode == 2),
+                           bilinear=bilinear)
         A, b, nv, sr2 = res[:4]
         assert (nv, sr2) == (t.n_valid, t.sum_r2), (lvl, t.k)
-        err = f32(np.float64(f32(1.0 / nv)) * np.float64(sr2 if mode == 0 else res[4]))
+        err = f32(np.float64(f32(1.0 / nv)) *
+                  np.float64(sr2 if (mode == 0 and not bilinear) else res[4]))
         assert err == f32(t.error)
         if not t.broke:
             assert np.array_equal(A, np.array(t.A[:], f32).reshape(6, 6)), (lvl, t.k)
