@@ -578,7 +578,7 @@ int uwt_profile_read(uwt_tracker* t, double ms[UWT_K_COUNT], long long launches[
 
 static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t* dev_src,
                           size_t row_stride, size_t frame_stride) {
-  ArgRegion* r;
+  ArgRegion* r = nullptr;
   int rc = acquire(t, &r);
   if (rc) return rc;
   rc = push_slots(t, r, n, slots, nullptr);
@@ -671,7 +671,7 @@ int uwt_upload_depth_frames(uwt_tracker* t, int n, const int* slots, const uint1
                                   row_stride, w * sizeof(uint16_t), h, cudaMemcpyDefault,
                                   t->stream));  // host or device-resident depth frames (UVA)
   }
-  ArgRegion* r;
+  ArgRegion* r = nullptr;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
   ProfSpan span(t, UWT_K_PYRAMID);
@@ -759,7 +759,7 @@ int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {
     if (!t->slots[slots[i]].pyramid)
       return fail(t, UWT_E_STATE, "slot %d has no frame", slots[i]);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  ArgRegion* r;
+  ArgRegion* r = nullptr;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
   ProfSpan span(t, UWT_K_GRADIENT);
@@ -791,7 +791,7 @@ int uwt_select_candidates(uwt_tracker* t, int n, const int* slots) {
       return fail(t, UWT_E_STATE, "slot %d has no depth frame (call uwt_upload_depth_frames)",
                   slots[i]);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  ArgRegion* r;
+  ArgRegion* r = nullptr;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
   ProfSpan span(t, UWT_K_CANDIDATES);
@@ -854,7 +854,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
       s.nranks = 1;
       s.prev_slot = prev_slots[0];
       s.cur_slot = cur_slots[0];
-      ArgRegion* r;
+      ArgRegion* r = nullptr;
       if ((rc = acquire(t, &r))) return rc;
       static_assert(sizeof(ShardState) <= sizeof(float) * 7 * 16, "staging too small");
       if ((size_t)t->cfg.max_frames * 7 * sizeof(float) >= sizeof(ShardState)) {
@@ -886,7 +886,7 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
       return UWT_OK;
     }
   }
-  ArgRegion* r;
+  ArgRegion* r = nullptr;
   if ((rc = acquire(t, &r))) return rc;
   if ((rc = push_slots(t, r, n, prev_slots, cur_slots))) return rc;
   if (init_poses7) {
@@ -1194,7 +1194,7 @@ static int complete_levels(uwt_tracker* t, int slot, int level, bool need_candid
   const bool do_grad = s.gradient && !s.gradient_all;
   const bool do_cand = need_candidates && s.candidates && !s.candidates_all;
   if (!do_grad && !do_cand) return UWT_OK;
-  ArgRegion* r;
+  ArgRegion* r = nullptr;
   int rc = acquire(t, &r);
   if (rc) return rc;
   if ((rc = push_slots(t, r, 1, &slot, nullptr))) return rc;
@@ -1249,7 +1249,7 @@ int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t*
     int16_t* tmp = nullptr;
     const size_t pe = t->geom.plane_elems;
     UWT_CUDA(t, cudaMalloc(&tmp, 2 * pe * sizeof(int16_t)));
-    ArgRegion* r;
+    ArgRegion* r = nullptr;
     if ((rc = acquire(t, &r))) { cudaFree(tmp); return rc; }
     if ((rc = push_slots(t, r, 1, &slot, nullptr))) { cudaFree(tmp); return rc; }
     const int k = launch_gradient(t->geom, t->pools, 1, r->d_int, t->stream,
