@@ -10,7 +10,13 @@ in the direct order:
 `value`  : tracks/s with the new frames already resident in HBM when the step starts.
 `e2e`    : the same loop through the C ABI with frames in pinned HOST memory: the H2D copy of
            every frame and the D2H read of every pose are inside the timed region.
-`--impl reference`: the CPU oracle (restatement of the reference, oracle/) on all host cores.
+`--impl reference`: the CPU oracle (restatement of the reference, oracle/) on all host cores, on
+           the SAME sequences (seeds, frames, K, W) as one GPU of `--impl ours`: identical
+           `config`.  Every rank of `--impl ours` tracks the same B seeded sequences (weak
+           scaling with fixed per-GPU work); `per_rank` lists every rank's own time, kernel
+           table, sweeps and clocks, so a slow rank is attributable.
+`secondary`: BASELINE configs 1 / 3 / 4 (EuRoC single stream, 8192 pairs split over the ranks,
+           one 3840x2160 pair sharded over the ranks) measured after the timed loops.
 
 Launch: python bench.py [--gpus N --steps K --warmup W]   (N > 1: under torchrun, one rank
 per GPU, weak scaling: every rank tracks its own B sequences, no data-path collective).
@@ -185,68 +191,136 @@ def ncu_traffic(batch):
     return None
 
 
-def cpu_tracks(frames_np, threads, accum_mode=0, weight_mode=0):
-    """Runs the oracle's reference-shaped loop on [n_seq, n_frames, H, W] host frames with
-    `threads` concurrent single-threaded trackers.  Returns (tracks, seconds, poses)."""
-    from oracle import uw_oracle as O
-    O.build()
-    w, h, fx, fy, cx, cy = synth.CALIB[CALIB]
-    nseq = frames_np.shape[0]
-    poses = [None] * nseq
-    O.lib()
+def workload_config(world, B, K, W):
+    """The workload both arms run, as the `config` object of the JSON line (identical keys and
+    values in `--impl ours` and `--impl reference` for the same --gpus/--steps/--warmup/--batch)."""
+    w, h = synth.CALIB[CALIB][:2]
+    return {"workload": "tum_mono_1280x1024_seq", "sequences_per_gpu": B,
+            "tracks_per_step": world * B, "tracked_frames_per_sequence": W + K,
+            "seeds": "sequence i of every GPU = texture/motion seed i (frame 0 prepared "
+                     "before the timed span, then one track per step)",
+            "levels": 5, "optimised_levels": "4..1",
+            "candidates": "all pixels with g > mean+20", "weights": "identity",
+            "l2_policy": "inputs larger than L2 (%.0f MB of new frames + %.1f GB working set "
+                         "per step and GPU)" % (B * w * h / 1e6, 2 * B * 21e6 / 1e9),
+            "parallelism": "independent sequences, %d per GPU, no comms" % B}
 
-    def work(ids):
-        p = O.default_params(w, h, fx, fy, cx, cy, accum_mode=accum_mode, threads=1,
-                             weight_mode=weight_mode)
-        for s in ids:
-            poses[s], _, _ = O.track_sequence(p, frames_np[s])
 
-    groups = [list(range(i, nseq, threads)) for i in range(threads)]
-    ths = [threading.Thread(target=work, args=(g,)) for g in groups if g]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    dt = time.perf_counter() - t0
-    return nseq * (frames_np.shape[1] - 1), dt, poses
+class CpuTrackers:
+    """The oracle's reference-shaped loop (oracle/uw_oracle.cpp uwo_stream_*: the previous
+    frame is kept between calls like System keeps it, main_uw_slam.cpp:139-151) for many
+    sequences on a pool of host threads, advanced one frame per step.  Frame 0 of every
+    sequence is prepared in the constructor, outside any timed span."""
+
+    def __init__(self, frames0, threads, weight_mode=0):
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import uw_oracle as O
+        O.build()
+        O.lib()
+        w, h, fx, fy, cx, cy = synth.CALIB[CALIB]
+        self.n = frames0.shape[0]
+        self.threads = max(1, min(threads, self.n))
+        self.params = [O.default_params(w, h, fx, fy, cx, cy, threads=1, weight_mode=weight_mode)
+                       for _ in range(self.n)]
+        self.pool = ThreadPoolExecutor(max_workers=self.threads)
+        self.groups = [list(range(i, self.n, self.threads)) for i in range(self.threads)]
+        self.streams = [None] * self.n
+
+        def mk(ids):
+            for s in ids:
+                self.streams[s] = O.Stream(self.params[s], frames0[s])
+        list(self.pool.map(mk, self.groups))
+
+    def step(self, frames):
+        """frames: u8 [n, H, W] (the next frame of every sequence).  Returns (poses [n,7],
+        wall seconds of the step).  ctypes releases the GIL: the threads run in parallel."""
+        poses = np.empty((self.n, 7), np.float32)
+
+        def work(ids):
+            for s in ids:
+                poses[s] = self.streams[s].track(frames[s])
+        t0 = time.perf_counter()
+        list(self.pool.map(work, self.groups))
+        return poses, time.perf_counter() - t0
+
+    def close(self):
+        for s in self.streams:
+            if s is not None:
+                s.close()
+        self.pool.shutdown()
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's tracker (oracle/; the
+    reference itself is not buildable here) on the SAME sequences as rank 0 of
+    `--impl ours` (same seeds, same frames, same K and W), one step = every sequence advanced
+    by one frame, all host threads busy, one single-threaded tracker per sequence."""
     rank, local_rank, world = dist_env()
     if rank != 0:
         return 0
     import torch
     threads = os.cpu_count() or 1
     dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
-    per_step = 2 * threads  # bounded sample: two tracks per host thread per step
-    n_steps = args.warmup + args.steps
-    # every step tracks `per_step` fresh frame pairs (sequence length 2)
-    seeds = list(range(10_000, 10_000 + per_step))
-    fr = gen_sequences(torch, dev, seeds, 2).permute(1, 0, 2, 3).contiguous().cpu().numpy()
+    B, K, W = args.batch, args.steps, args.warmup
+    seeds = list(range(B))
+    fr = gen_sequences(torch, dev, seeds, 1 + W + K).cpu().numpy()      # [frames, B, H, W]
+    trk = CpuTrackers(fr[0], threads)
     times = []
-    for s in range(n_steps):
-        n, dt, _ = cpu_tracks(fr, threads)
-        if s >= args.warmup:
+    for i in range(1, 1 + W + K):
+        _, dt = trk.step(fr[i])
+        if i > W:
             times.append(dt)
+    trk.close()
     total = sum(times)
-    value = per_step * args.steps / total
+    value = B * K / total
+    # the single-thread figure (the reference is single-threaded): a bounded sample of the
+    # same sequences, same steps
+    n1 = min(B, args.cpu_sequences_1t)
+    trk1 = CpuTrackers(fr[0][:n1], 1)
+    t1 = 0.0
+    for i in range(1, 1 + W + K):
+        _, dt = trk1.step(fr[i][:n1])
+        if i > W:
+            t1 += dt
+    trk1.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tracks/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * total / max(K, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+f64acc", "data": "synthetic",
-        "config": {"workload": "tum_mono_1280x1024_seq", "tracks_per_step": per_step,
-                   "levels": 5, "optimised_levels": "4..1"},
-        "cpu_baseline": {"value": value, "unit": "tracks/s", "cores": threads, "kind": "port",
-                         "sample": "%d tracks/step x %d steps, one single-threaded oracle "
-                                   "tracker per host thread" % (per_step, args.steps)},
+        "config": workload_config(args.gpus, B, K, W),
+        "cpu_baseline": {"value": value, "unit": "tracks/s", "cores": trk.threads, "kind": "port",
+                         "sample": "the %d sequences of one GPU x %d steps (%d tracks, %.1f s): "
+                                   "oracle port of the reference tracker, one single-threaded "
+                                   "tracker per sequence on %d host threads; at --gpus N > 1 the "
+                                   "job has N x %d sequences per step, of which this is one "
+                                   "GPU's share" % (B, K, B * K, total, trk.threads, B),
+                         "single_thread_value": n1 * K / t1 if t1 > 0 else None,
+                         "single_thread_sample": "%d of those sequences x %d steps" % (n1, K)},
         "e2e": {"value": value, "unit": "tracks/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=args.out, flush=True)
     return 0
+
+
+def h2d_ceiling(torch, dist, dev, host, world, reps=8):
+    """What the host can feed: every rank copies `reps` x one step's frames (the same pinned
+    buffers the e2e loop uploads) to its GPU with plain cudaMemcpyAsync, all ranks at once.
+    Returns GB/s of this rank."""
+    dst = torch.empty_like(host[0], device=dev)
+    dst.copy_(host[0], non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        dst.copy_(host[1 + i % (host.shape[0] - 1)], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return reps * host[0].numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
 
 def run_ours(args):
@@ -266,7 +340,10 @@ def run_ours(args):
     n_frames = 1 + W + K + 1  # +1: the e2e loop uploads one frame ahead
 
     # ---- synthetic sequences (device + pinned host copies) ----
-    seeds = [rank * 100_000 + i for i in range(B)]
+    # Weak scaling with fixed per-GPU work: every rank tracks the same B seeded sequences, so
+    # the per-rank times differ only by what the hardware does (and --impl reference tracks
+    # exactly one GPU's share of the job).
+    seeds = list(range(B))
     frames = gen_sequences(torch, dev, seeds, n_frames)          # [n_frames, B, H, W]
     host = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)
     host.copy_(frames)
@@ -319,20 +396,19 @@ def run_ours(args):
         upload, one track and (e2e) one pose read."""
         prime()
         prev, cur = slots_a, slots_b
-        stats_acc = []
+        stats_acc, all_poses = [], []
         upload(1, cur, from_host)
         for i in range(1, 1 + W):
             track(prev, cur)
             upload(i + 1, prev, from_host)   # next step's frames go where `prev` lives
             if fetch_poses:
-                fetch()
+                all_poses.append(fetch()[0])
             prev, cur = cur, prev
         barrier()
         t.profile(True)
         l0 = t.launch_count()
         sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wall0 = time.perf_counter()
         e0.record(stream)
@@ -341,30 +417,34 @@ def run_ours(args):
             upload(i + 1, prev, from_host)
             if fetch_poses:
                 stats_acc.append(fetch())
+                all_poses.append(stats_acc[-1][0])
             prev, cur = cur, prev
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - wall0
-        clocks = sampler.stop() if rank == 0 else None
-        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        ms_own = e0.elapsed_time(e1)
         prof = t.profile_read()
         launches = t.launch_count() - l0
         t.profile(False)
+        ms = ms_own
         if world > 1:
             tt = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        return ms, wall, prof, launches, clocks, stats_acc
+        return ms, ms_own, wall, prof, launches, clocks, stats_acc, all_poses
 
     # ---- value: inputs resident in HBM ----
-    ms, wall, prof, launches, clocks, _ = timed_loop(from_host=False, fetch_poses=False)
+    ms, ms_own, wall, prof, launches, clocks, _, _ = timed_loop(from_host=False, fetch_poses=False)
     # ---- e2e: pinned host frames in, poses out, every step ----
-    ms_e, wall_e, prof_e, launches_e, clocks_e, stats_acc = timed_loop(from_host=True, fetch_poses=True)
+    ms_e, ms_e_own, wall_e, prof_e, launches_e, clocks_e, stats_acc, all_poses = \
+        timed_loop(from_host=True, fetch_poses=True)
+    # ---- what the host side can feed at this N (all ranks copying at once) ----
+    ceiling_gbs = h2d_ceiling(torch, dist, dev, host, world)
 
     # algorithmic bytes of the estimate kernel: 10 B x points x residual sweeps (both loops
     # process the same frames, so the sweeps counted in the e2e loop hold for the value loop)
     point_evals = 0
-    evals_hist = np.zeros(8, np.int64)
     sweeps = 0
     for out, st in stats_acc:
         for s in st:
@@ -400,6 +480,20 @@ def run_ours(args):
     kernels["estimate"]["us_per_gn_sweep_per_problem"] = \
         1e3 * est_ms * B / max(sweeps, 1) if sweeps else None
 
+    # ---- per-rank attribution (the job's time is the MAX over ranks) ----
+    mine = {"rank": rank, "ms_per_step": ms_own / K, "e2e_ms_per_step": ms_e_own / K,
+            "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+            "sweeps_per_track": sweeps / max(len(stats_acc) * B, 1),
+            "point_evals_per_step": point_evals / max(K, 1),
+            "sm_mhz": clocks["sm_mhz"], "e2e_sm_mhz": clocks_e["sm_mhz"],
+            "clock_reasons": sorted(set(clocks["reasons"]) | set(clocks_e["reasons"])),
+            "h2d_ceiling_gbs": ceiling_gbs,
+            "e2e_h2d_gbs": B * n0 / (ms_e_own / K * 1e-3) / 1e9}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+
     # ---- single-problem latency: one pair alone on the GPU (16-CTA cluster) ----
     prime()
     upload(1, slots_b, False)
@@ -421,61 +515,143 @@ def run_ours(args):
     if rank == 0:
         value = world * B * K / (ms * 1e-3)
         e2e_value = world * B * K / (ms_e * 1e-3)
+        ceil_min = min(p["h2d_ceiling_gbs"] for p in per_rank)
+        e2e_gbs = B * n0 / (ms_e / K * 1e-3) / 1e9
+        cluster_form = args.cluster_kernel or args.cluster or args.dmma_accum
         line = {
             "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64acc", "data": "synthetic",
-            "config": {"workload": "tum_mono_1280x1024_seq", "sequences_per_gpu": B,
-                       "tracks_per_step": world * B, "levels": 5, "optimised_levels": "4..1",
-                       "candidates": "all pixels with g > mean+20",
-                       "l2_policy": "inputs larger than L2 (%.0f MB of new frames + %.1f GB "
-                                    "working set per step)" % (B * n0 / 1e6,
-                                                                 2 * B * 21e6 / 1e9),
-                       "cluster_size": args.cluster,
-                       "estimate_kernel": ("cluster" if (args.cluster_kernel or args.cluster or
-                                                         args.dmma_accum)
-                                           else "dataflow"),
-                       "weights": ["identity", "tukey_mad", "huber"][args.weights],
-                       "lazy_levels": bool(args.lazy_levels),
-                       "host_numa_node_of_rank0": numa_node,
-                       "parallelism": "independent sequences, %d per GPU, no comms" % B},
+            "config": workload_config(world, B, K, W),
+            "impl_config": {"cluster_size": args.cluster,
+                            "estimate_kernel": "cluster" if cluster_form else "dataflow",
+                            "weights": ["identity", "tukey_mad", "huber"][args.weights],
+                            "lazy_levels": bool(args.lazy_levels),
+                            "host_numa_node_of_rank0": numa_node},
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": ms_e / K,
                     "h2d_bytes_per_step": B * n0, "d2h_bytes_per_step":
-                    B * (7 * 4 + 4 * 4 * 7)},
+                    B * (7 * 4 + 4 * 4 * 7),
+                    "h2d_gbs_per_gpu": e2e_gbs,
+                    "h2d_ceiling_gbs_per_gpu": ceil_min,
+                    "h2d_ceiling_gbs_aggregate": sum(p["h2d_ceiling_gbs"] for p in per_rank),
+                    "frac_of_h2d_ceiling": e2e_gbs / ceil_min if ceil_min else None,
+                    "note": "ceiling = all %d ranks copying one step's pinned frames with "
+                            "plain cudaMemcpyAsync at the same time (slowest rank)" % world},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": ("estimate_kernel (cluster)"
-                                    if (args.cluster_kernel or args.cluster or args.dmma_accum)
+            "roofline": {"kernel": ("estimate_kernel (cluster)" if cluster_form
                                     else "estimate_flow_kernel"),
                          "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(B),
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": est_ms / est_calls,
-                         "point_evals_per_launch": point_evals / est_calls},
+                         "point_evals_per_launch": point_evals / est_calls,
+                         "real_bound": issue_bound(point_evals / est_calls, est_ms / est_calls,
+                                                   clocks["sm_mhz"])},
             "kernels": kernels,
+            "per_rank": per_rank,
             "gn_iteration_us": gn_us,
             "wall_s": {"value_loop": wall, "e2e_loop": wall_e},
         }
         if world == 1 and not args.no_cpu_baseline:
-            # bounded CPU sample of the same workload: the first `nseq` sequences, all K+W steps
+            # bounded CPU sample of the same workload: the first `nseq` sequences, all W+K steps,
+            # one thread (the reference is single-threaded)
             nseq = min(B, args.cpu_sequences)
-            fr = host[:1 + W + K, :nseq].permute(1, 0, 2, 3).contiguous().numpy()
-            n, dt, poses = cpu_tracks(fr, 1, weight_mode=args.weights)
+            fr = host[:1 + W + K, :nseq].numpy()
+            trk = CpuTrackers(fr[0], 1, weight_mode=args.weights)
+            dt, bad, cmp_n = 0.0, 0, 0
+            for i in range(1, 1 + W + K):
+                poses, d = trk.step(fr[i])
+                dt += d
+                gpu = all_poses[i - 1]
+                for s in range(nseq):
+                    cmp_n += 1
+                    bad += 0 if np.array_equal(poses[s], gpu[s]) else 1
+            trk.close()
+            n = nseq * (W + K)
             line["cpu_baseline"] = {
                 "value": n / dt, "unit": "tracks/s", "cores": 1, "kind": "port",
-                "sample": "%d sequences x %d frames of this workload (%d tracks, %.1f s), "
-                          "single-threaded oracle" % (nseq, 1 + W + K, n, dt)}
-            # bonus: the oracle's last pose of every sampled sequence vs the GPU's e2e result
-            gpu_last = stats_acc[-1][0]
-            same = all(np.array_equal(poses[s][-1], gpu_last[s]) for s in range(nseq))
-            line["cpu_baseline"]["gpu_pose_bit_identical_on_sample"] = bool(same)
-        print(json.dumps(line), file=args.out, flush=True)
+                "sample": "%d sequences x %d tracked frames of this workload (%d tracks, %.1f s), "
+                          "single-threaded oracle" % (nseq, W + K, n, dt),
+                "gpu_pose_bit_identical_on_sample": bad == 0}
+            line["parity_sample"] = {"tracks_compared": cmp_n, "pose_mismatches": bad,
+                                     "what": "every pose of every warm-up and timed e2e step of "
+                                             "the sampled sequences, GPU vs oracle, bit for bit",
+                                     "soak": soak_record()}
     t.close()
+    del frames, host
+    torch.cuda.empty_cache()
+    # ---- BASELINE configs 1 / 3 / 4 in the same record ----
+    if not args.no_secondary:
+        sec = run_secondary(args, torch, dist, rank, local_rank, world)
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def issue_bound(points_per_launch, launch_ms, sm_mhz):
+    """K4 against the roof that actually bounds it.  Per point the sweep issues
+    K4_INSTR_PER_POINT SASS instructions (profiles/: per-pipe histogram of the hot loop), of
+    which K4_FP64_PER_POINT go to the fp64 pipe; an SM issues 4 warp instructions per clock
+    (128 thread-instructions) and retires 42.3 DFMA lanes per clock
+    (profiles/r01_microbench_fp64.txt)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k4_instruction_mix.json")) as f:
+            mix = json.load(f)
+    except Exception:
+        return None
+    clk = (sm_mhz or 1965.0) * 1e6
+    sms = 148
+    t_issue = points_per_launch * mix["instructions_per_point"] / (128.0 * sms * clk)
+    t_fp64 = points_per_launch * (mix["dfma_per_point"] / 42.3 +
+                                  mix["dadd_dmul_per_point"] / 63.6) / (sms * clk)
+    return {"bound": "issue", "issue_bound_ms": 1e3 * t_issue, "fp64_pipe_bound_ms": 1e3 * t_fp64,
+            "frac_of_issue_bound": 1e3 * t_issue / launch_ms if launch_ms else None,
+            "frac_of_fp64_bound": 1e3 * t_fp64 / launch_ms if launch_ms else None,
+            "instructions_per_point": mix["instructions_per_point"],
+            "source": "profiles/k4_instruction_mix.json"}
+
+
+def soak_record():
+    """The committed result of the long parity soak (tools/parity_soak.py, run on a B200 box);
+    bench.py only cites it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "parity_soak.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_secondary(args, torch, dist, rank, local_rank, world):
+    """BASELINE configs 1 (EuRoC single stream), 3 (8192 pairs, strong split over the ranks) and
+    4 (one 3840x2160 pair sharded over the ranks) in the driver-visible record.  Every entry is
+    computed by tools/bench_configs.py's functions; a failure becomes {"error": ...} instead of
+    losing the headline line."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "bench_configs", os.path.join(ROOT, "tools", "bench_configs.py"))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    out = {}
+    for name, fn, ns in (
+            ("config1_euroc_single_stream", bc.euroc_seq, bc.Args()),
+            ("config3_batch8192_640x480", bc.batch8192, bc.Args(pairs=args.secondary_pairs)),
+            ("config4_shard4k", bc.shard4k, bc.Args(reps=20, check=True))):
+        try:
+            res = fn(ns, torch, dist, rank, local_rank, world)
+        except Exception as e:  # noqa: BLE001
+            res = {"error": "%s: %s" % (type(e).__name__, e)}
+        out[name] = res
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    return out
 
 
 def main():
@@ -497,7 +673,12 @@ def main():
                     help="residual weights: 0 identity (reference), 1 Tukey/MAD, 2 Huber")
     ap.add_argument("--cpu-sequences", type=int, default=24,
                     help="sequences of the workload the single-threaded CPU baseline tracks (~12 s)")
+    ap.add_argument("--cpu-sequences-1t", type=int, default=8,
+                    help="--impl reference: sequences of the single-thread sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip BASELINE configs 1/3/4 (the `secondary` block)")
+    ap.add_argument("--secondary-pairs", type=int, default=8192)
     args = ap.parse_args()
     args.out = claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -287,7 +287,9 @@ int uwt_get_candidates(uwt_tracker* t, int slot, int level, float* pts4, int cap
  *   0..11 x | 12..23 y | 24..31 I1 = images_[l](y,x) | 32..44 gradientX_[l](y,x) (13-bit two's
  *   complement) | 45..57 gradientY_[l](y,x) | 58..63 zero. */
 int uwt_get_records(uwt_tracker* t, int slot, int level, uint64_t* packed, int capacity, int* n);
-/* Trace of problem `index` of the last uwt_estimate_pose (needs UWT_FLAG_TRACE). */
+/* Trace of problem `index` of the last uwt_estimate_pose (needs UWT_FLAG_TRACE).  Traces are
+ * recorded for batches of at most 64 problems; after a larger batch (not traced) the call returns
+ * UWT_E_STATE instead of an earlier batch's rows. */
 int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, int* n);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 long long uwt_launch_count(const uwt_tracker* t);

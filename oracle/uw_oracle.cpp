@@ -1062,78 +1062,115 @@ int uwo_track_pair(const uwo_params* p, const uint8_t* prev0, const uint8_t* cur
 
 
 // One reference-shaped tracking loop over a frame sequence (System::AddFrame +
-// System::Tracking in the direct order).  Frame 0 is only prepared; every
-// later frame i costs exactly one "track": pyramid(i), EstimatePose(i-1, i),
-// ApplyGradient(i), ObtainCandidatePoints(i).  poses_out: (n_frames-1) x 7;
-// seconds_out (optional): per-track wall seconds, (n_frames-1) entries.
+// System::Tracking in the direct order), as a stateful stream: the object holds
+// what `System` keeps between frames (the previous uw::Frame with its pyramid, gradients and
+// candidate points).  uwo_stream_create prepares frame 0; every uwo_stream_track costs exactly
+// one "track": pyramid(i), EstimatePose(i-1, i), ApplyGradient(i), ObtainCandidatePoints(i)
+// (main_uw_slam.cpp:139-151 / System.cpp:193-223).
+}  // extern "C"
+
+namespace {
+struct StreamFrame {
+  std::vector<std::vector<uint8_t>> img, g;
+  std::vector<std::vector<int16_t>> gx, gy;
+  std::vector<std::vector<float>> cand;
+  std::vector<int> ncand;
+};
+void stream_pyramid(const uwo_params& p, StreamFrame& f, const uint8_t* l0) {
+  const int L = p.levels;
+  f.img.resize(L);
+  for (int l = 0; l < L; ++l) {
+    const size_t n = (size_t)(p.width >> l) * (p.height >> l);
+    f.img[l].resize(n);
+    if (l == 0)
+      std::memcpy(f.img[0].data(), l0, n);
+    else
+      uwo_pyr_down(f.img[l - 1].data(), p.width >> (l - 1), p.height >> (l - 1), f.img[l].data());
+  }
+}
+void stream_gradient_candidates(const uwo_params& p, StreamFrame& f) {
+  const int L = p.levels;
+  f.g.resize(L); f.gx.resize(L); f.gy.resize(L); f.cand.resize(L); f.ncand.assign(L, 0);
+  for (int l = 0; l < L; ++l) {
+    const int w = p.width >> l, h = p.height >> l;
+    f.gx[l].resize((size_t)w * h);
+    f.gy[l].resize((size_t)w * h);
+    f.g[l].resize((size_t)w * h);
+    uwo_scharr(f.img[l].data(), w, h, f.gx[l].data(), f.gy[l].data());
+    uwo_gradmag(f.gx[l].data(), f.gy[l].data(), (long long)w * h, f.g[l].data());
+  }
+  for (int l = 0; l < L; ++l) {
+    const int w = p.width >> l, h = p.height >> l;
+    f.cand[l].resize((size_t)w * h * 4);
+    f.ncand[l] = uwo_candidates(f.g[l].data(), w, h, p.gradient_threshold, f.cand[l].data(),
+                                nullptr, nullptr);
+  }
+}
+}  // namespace
+
+struct uwo_stream {
+  uwo_params p;
+  StreamFrame a, b;
+  StreamFrame* prev;
+  StreamFrame* cur;
+};
+
+extern "C" {
+
+uwo_stream* uwo_stream_create(const uwo_params* p, const uint8_t* frame0) {
+  uwo_stream* s = new (std::nothrow) uwo_stream();
+  if (!s) return nullptr;
+  s->p = *p;
+  s->prev = &s->a;
+  s->cur = &s->b;
+  stream_pyramid(s->p, *s->prev, frame0);
+  stream_gradient_candidates(s->p, *s->prev);
+  return s;
+}
+
+void uwo_stream_destroy(uwo_stream* s) { delete s; }
+
+int uwo_stream_track(uwo_stream* s, const uint8_t* frame, float* out_pose7, uwo_stats* stats) {
+  const uwo_params* p = &s->p;
+  const int L = p->levels;
+  stream_pyramid(*p, *s->cur, frame);
+  const uint8_t* pp[UWO_MAX_LEVELS];
+  const uint8_t* cp[UWO_MAX_LEVELS];
+  const int16_t* gxp[UWO_MAX_LEVELS];
+  const int16_t* gyp[UWO_MAX_LEVELS];
+  const float* cd[UWO_MAX_LEVELS];
+  for (int l = 0; l < L; ++l) {
+    pp[l] = s->prev->img[l].data();
+    cp[l] = s->cur->img[l].data();
+    gxp[l] = s->prev->gx[l].data();
+    gyp[l] = s->prev->gy[l].data();
+    cd[l] = s->prev->cand[l].data();
+  }
+  int rc = uwo_estimate_pose(p, pp, cp, gxp, gyp, cd, s->prev->ncand.data(), nullptr, out_pose7,
+                             stats, nullptr, 0, nullptr);
+  if (rc) return rc;
+  stream_gradient_candidates(*p, *s->cur);
+  std::swap(s->prev, s->cur);
+  return 0;
+}
+
+// The same loop over a whole sequence held in memory.  poses_out: (n_frames-1) x 7;
+// seconds_out (optional): per-track wall seconds, (n_frames-1) entries (frame 0's preparation
+// is outside every one of them).
 int uwo_track_sequence(const uwo_params* p, const uint8_t* frames, int n_frames,
                        float* poses_out, double* seconds_out, uwo_stats* stats_out) {
-  const int L = p->levels;
-  struct FrameBuf {
-    std::vector<std::vector<uint8_t>> img, g;
-    std::vector<std::vector<int16_t>> gx, gy;
-    std::vector<std::vector<float>> cand;
-    std::vector<int> ncand;
-  };
-  auto prepare_pyr = [&](FrameBuf& f, const uint8_t* l0) {
-    f.img.resize(L);
-    for (int l = 0; l < L; ++l) {
-      const size_t n = (size_t)(p->width >> l) * (p->height >> l);
-      f.img[l].resize(n);
-      if (l == 0)
-        std::memcpy(f.img[0].data(), l0, n);
-      else
-        uwo_pyr_down(f.img[l - 1].data(), p->width >> (l - 1), p->height >> (l - 1),
-                     f.img[l].data());
-    }
-  };
-  auto prepare_grad = [&](FrameBuf& f) {
-    f.g.resize(L); f.gx.resize(L); f.gy.resize(L); f.cand.resize(L); f.ncand.assign(L, 0);
-    for (int l = 0; l < L; ++l) {
-      const int w = p->width >> l, h = p->height >> l;
-      f.gx[l].resize((size_t)w * h);
-      f.gy[l].resize((size_t)w * h);
-      f.g[l].resize((size_t)w * h);
-      uwo_scharr(f.img[l].data(), w, h, f.gx[l].data(), f.gy[l].data());
-      uwo_gradmag(f.gx[l].data(), f.gy[l].data(), (long long)w * h, f.g[l].data());
-    }
-    for (int l = 0; l < L; ++l) {
-      const int w = p->width >> l, h = p->height >> l;
-      f.cand[l].resize((size_t)w * h * 4);
-      f.ncand[l] = uwo_candidates(f.g[l].data(), w, h, p->gradient_threshold, f.cand[l].data(),
-                                  nullptr, nullptr);
-    }
-  };
   const size_t fsz = (size_t)p->width * p->height;
-  FrameBuf a, b;
-  FrameBuf* prev = &a;
-  FrameBuf* cur = &b;
-  prepare_pyr(*prev, frames);
-  prepare_grad(*prev);
-  for (int i = 1; i < n_frames; ++i) {
+  uwo_stream* s = uwo_stream_create(p, frames);
+  if (!s) return -1;
+  int rc = 0;
+  for (int i = 1; i < n_frames && rc == 0; ++i) {
     const double t0 = now_s();
-    prepare_pyr(*cur, frames + (size_t)i * fsz);
-    const uint8_t* pp[UWO_MAX_LEVELS];
-    const uint8_t* cp[UWO_MAX_LEVELS];
-    const int16_t* gxp[UWO_MAX_LEVELS];
-    const int16_t* gyp[UWO_MAX_LEVELS];
-    const float* cd[UWO_MAX_LEVELS];
-    for (int l = 0; l < L; ++l) {
-      pp[l] = prev->img[l].data();
-      cp[l] = cur->img[l].data();
-      gxp[l] = prev->gx[l].data();
-      gyp[l] = prev->gy[l].data();
-      cd[l] = prev->cand[l].data();
-    }
-    int rc = uwo_estimate_pose(p, pp, cp, gxp, gyp, cd, prev->ncand.data(), nullptr,
-                               poses_out + (size_t)(i - 1) * 7,
-                               stats_out ? stats_out + (i - 1) : nullptr, nullptr, 0, nullptr);
-    if (rc) return rc;
-    prepare_grad(*cur);
+    rc = uwo_stream_track(s, frames + (size_t)i * fsz, poses_out + (size_t)(i - 1) * 7,
+                          stats_out ? stats_out + (i - 1) : nullptr);
     if (seconds_out) seconds_out[i - 1] = now_s() - t0;
-    std::swap(prev, cur);
   }
-  return 0;
+  uwo_stream_destroy(s);
+  return rc;
 }
 
 }  // extern "C"

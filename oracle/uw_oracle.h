@@ -189,6 +189,15 @@ int uwo_gn_update(const uwo_params* p, const double* sums32, int k, float* pose7
 int uwo_track_pair(const uwo_params* p, const uint8_t* prev0, const uint8_t* cur0,
                    float* out_pose7, uwo_stats* stats, double* seconds4);
 
+/* The reference's outer loop (main_uw_slam.cpp:139-151: AddFrame + Tracking per frame) as a
+ * stateful stream: create() prepares frame 0 (pyramid, ApplyGradient, ObtainCandidatePoints);
+ * track() is one track = pyramid(i), EstimatePose(i-1,i), ApplyGradient(i),
+ * ObtainCandidatePoints(i), and keeps frame i as the next `prev`. */
+typedef struct uwo_stream uwo_stream;
+uwo_stream* uwo_stream_create(const uwo_params* p, const uint8_t* frame0);
+void uwo_stream_destroy(uwo_stream* s);
+int uwo_stream_track(uwo_stream* s, const uint8_t* frame, float* out_pose7, uwo_stats* stats);
+
 /* Reference-shaped loop over a sequence of n_frames level-0 frames (contiguous, w*h bytes
  * each): one "track" per frame after the first = pyramid(i), EstimatePose(i-1,i),
  * ApplyGradient(i), ObtainCandidatePoints(i).  poses_out: (n_frames-1) x 7. */

@@ -477,6 +477,47 @@ def track_sequence(params, frames):
     return poses, secs, list(stats)
 
 
+class Stream:
+    """uwo_stream: the reference's per-frame loop with the previous frame kept between calls
+    (create = frame 0 prepared; track = one pose-track)."""
+
+    def __init__(self, params, frame0):
+        L = lib()
+        L.uwo_stream_create.restype = C.c_void_p
+        L.uwo_stream_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint8)]
+        L.uwo_stream_destroy.argtypes = [C.c_void_p]
+        L.uwo_stream_track.restype = C.c_int
+        L.uwo_stream_track.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float),
+                                       C.POINTER(Stats)]
+        self._L = L
+        self._params = params
+        f0 = np.ascontiguousarray(frame0, np.uint8)
+        self._h = L.uwo_stream_create(C.byref(params), _p(f0, C.c_uint8))
+        if not self._h:
+            raise MemoryError("uwo_stream_create")
+
+    def track(self, frame, with_stats=False):
+        f = np.ascontiguousarray(frame, np.uint8)
+        out = np.empty(7, np.float32)
+        st = Stats() if with_stats else None
+        rc = self._L.uwo_stream_track(self._h, _p(f, C.c_uint8), _p(out, C.c_float),
+                                      C.byref(st) if with_stats else None)
+        if rc != 0:
+            raise RuntimeError("uwo_stream_track failed: %d" % rc)
+        return (out, st) if with_stats else out
+
+    def close(self):
+        if self._h:
+            self._L.uwo_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def sweep_range(params, frame_prev, frame_cur, lvl, lo, hi, pose7):
     """uwo_sweep_range on FrameData: the 32 sums of candidate rows [lo, hi) of level lvl."""
     L = lib()

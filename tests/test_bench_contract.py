@@ -16,7 +16,8 @@ def run(args, env_extra=None):
 
 
 def test_reference_arm_prints_one_json_line():
-    r = run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    r = run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--batch", "4",
+             "--cpu-sequences-1t", "2"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -25,6 +26,11 @@ def test_reference_arm_prints_one_json_line():
     assert j["metric"].startswith("pose-tracks/sec @1280x1024")
     assert j["steps"] == 1 and j["warmup"] == 0 and j["n_gpus"] == 1 and j["value"] > 0
     assert j["config"]["workload"] == "tum_mono_1280x1024_seq"
+    assert j["config"]["sequences_per_gpu"] == 4 and j["config"]["tracks_per_step"] == 4
+    # the config object is built by the same function for both arms
+    sys.path.insert(0, ROOT)
+    import bench
+    assert j["config"] == bench.workload_config(1, 4, 1, 0)
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     e = j["e2e"]

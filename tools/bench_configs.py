@@ -29,6 +29,16 @@ sys.path.insert(0, ROOT)
 from uw_slam_b200 import synth  # noqa: E402
 
 
+class Args:
+    """Defaults of the command line below, for callers that import the workload functions
+    (bench.py's `secondary` block)."""
+
+    def __init__(self, **kw):
+        self.pairs, self.chunk, self.reps, self.check = 8192, 1024, 20, False
+        self.flags, self.weights, self.depth = 0, 0, 0
+        self.__dict__.update(kw)
+
+
 def env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
@@ -44,6 +54,8 @@ def make_tracker(calib, device, **cfg):
 
 
 def euroc_seq(args, torch, dist, rank, local_rank, world):
+    if rank != 0:   # a single camera stream does not shard: the other ranks have nothing to do
+        return None
     calib, n_frames, rekey = "euroc", 64, 8
     w, h = synth.CALIB[calib][:2]
     frames, _, _ = synth.render_sequence(calib, 11, n_frames, rot=1.5e-3, trans=1.5e-3)
@@ -90,6 +102,7 @@ def euroc_seq(args, torch, dist, rank, local_rank, world):
             key = O.FrameData(frames[i])
     cpu_dt = time.perf_counter() - t1
     est_ms, est_l = prof["estimate"]
+    t.close()
     return {"metric": "pose-tracks/sec, single stream 752x480 (frame-to-keyframe)",
             "value": (n_frames - 1) / dt, "unit": "tracks/s", "tracks": n_frames - 1,
             "ms_per_track_e2e": 1e3 * dt / (n_frames - 1),
@@ -122,7 +135,7 @@ def batch8192(args, torch, dist, rank, local_rank, world):
     cur = torch.empty_like(prev)
     for a in range(0, mine, 256):
         b = min(a + 256, mine)
-        p_, c_ = synth.render_batch_torch(calib, list(range(lo + a, lo + b)), dev)
+        p_, c_ = synth.render_pairs_torch(calib, list(range(lo + a, lo + b)), dev)
         prev[a:b], cur[a:b] = p_, c_
     ps, cs = list(range(chunk)), list(range(chunk, 2 * chunk))
     out = np.empty((mine, 7), np.float32)
@@ -167,6 +180,7 @@ def batch8192(args, torch, dist, rank, local_rank, world):
                                        O.FrameData(b, with_candidates=False))
             same &= bool(np.array_equal(op, out[i]))
         res["spot_check_bit_identical_to_oracle"] = same
+    t.close()
     return res
 
 
@@ -218,56 +232,81 @@ def hypotheses(args, torch, dist, rank, local_rank, world):
 
 
 def shard4k(args, torch, dist, rank, local_rank, world):
-    from uw_slam_b200.sharded import TrackerShardBackend, estimate_pose_sharded
+    """Config 4: ONE 3840x2160 pair, the candidate list of every level split over the ranks.
+    Three forms on the same pair, every one checked bit for bit against the others:
+      fused   : one persistent kernel per rank, all-reduce of the 32 fp64 sums through peer
+                (CUDA-IPC mapped) mailboxes inside the kernel
+      nccl    : per sweep accumulate kernel -> NCCL all-reduce -> update kernel, host loop
+      1 GPU   : the SAME fused kernel as a single-rank instance on rank 0's GPU alone
+                (uwt_estimate_pose's path for one large frame)"""
+    from uw_slam_b200.sharded import (TrackerShardBackend, connect_fused, estimate_pose_sharded,
+                                      estimate_pose_sharded_fused)
     calib = "uhd"
-    prev, cur, _, _ = synth.render_pair(calib, 21)
+    w, h = synth.CALIB[calib][:2]
+    dev = torch.device("cuda", local_rank)
+    # every rank must hold the same bytes: rank 0 renders, the others receive
+    pair = torch.empty((2, h, w), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        p_, c_ = synth.render_pairs_torch(calib, [21], dev)
+        pair[0], pair[1] = p_[0], c_[0]
+    if world > 1:
+        dist.broadcast(pair, src=0)
     t = make_tracker(calib, local_rank, max_frames=2)
-    t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.AddFramesDevice([0, 1], pair.data_ptr())
     t.ApplyGradient([0])
     t.ObtainCandidatePoints([0])
-    backend = TrackerShardBackend(t, 0, 1)
-    pose, stats, sweeps = estimate_pose_sharded(backend)
-    t.synchronize()
-    if world > 1:
-        dist.barrier()
     reps = args.reps
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        pose, stats, sweeps = estimate_pose_sharded(backend)
+
+    def timed(fn, sync):
+        fn()
+        sync()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        r2 = sync()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()), (r2 if r2 is not None else r)
+
+    # NCCL + host loop
+    backend = TrackerShardBackend(t, 0, 1)
+    dt_nccl, (pose, stats, sweeps) = timed(lambda: estimate_pose_sharded(backend),
+                                           lambda: t.synchronize())
+    # fused in-kernel all-reduce over the ranks
+    connect_fused(t)
+    dt_fused, (fpose, _) = timed(lambda: t.ShardEstimateFusedAsync(0, 1),
+                                 lambda: t.ShardEstimateFusedWait())
+    # the same kernel on one GPU (every rank runs its own copy; rank 0's figure is reported)
+    t.EstimatePose([0], [1])
     t.synchronize()
-    dt = (time.perf_counter() - t0) / reps
-    # the unsharded single-kernel path on the same pair (rank 0's GPU), for comparison
     t1 = time.perf_counter()
     for _ in range(reps):
         ref = t.EstimatePose([0], [1])
-    t.synchronize()
     dt_single = (time.perf_counter() - t1) / reps
-    # fused form: one persistent kernel per rank, all-reduce over peer memory inside the kernel
-    from uw_slam_b200.sharded import connect_fused, estimate_pose_sharded_fused
-    connect_fused(t)
-    fpose, _ = estimate_pose_sharded_fused(t, 0, 1)
-    if world > 1:
-        dist.barrier()
-    t2 = time.perf_counter()
-    for _ in range(reps):
-        t.ShardEstimateFusedAsync(0, 1)
-    fpose, _ = t.ShardEstimateFusedWait()
-    dt_fused = (time.perf_counter() - t2) / reps
     res = {"metric": "GN pose estimate of one 3840x2160 pair, candidate list sharded over ranks",
+           "n_gpus": world, "sweeps": sweeps, "points_per_level": list(stats.n_points)[:5],
            "ms_per_estimate_fused_peer_allreduce": 1e3 * dt_fused,
            "us_per_sweep_fused": 1e6 * dt_fused / sweeps,
-           "fused_pose_equals_single_gpu_kernel": bool(np.array_equal(fpose, ref[0])),
-           "n_gpus": world, "ms_per_estimate_sharded": 1e3 * dt, "sweeps": sweeps,
-           "us_per_sweep_sharded": 1e6 * dt / sweeps,
-           "ms_per_estimate_single_kernel_1gpu": 1e3 * dt_single,
-           "points_per_level": list(stats.n_points)[:5],
-           "pose_equals_single_gpu_kernel": bool(np.array_equal(pose, ref[0])),
-           "collective": "none" if world == 1 else "NCCL all-reduce of 32 fp64 per sweep"}
+           "ms_per_estimate_nccl_host_loop": 1e3 * dt_nccl,
+           "us_per_sweep_nccl_host_loop": 1e6 * dt_nccl / sweeps,
+           "ms_per_estimate_same_fused_kernel_1gpu": 1e3 * dt_single,
+           "us_per_sweep_same_fused_kernel_1gpu": 1e6 * dt_single / sweeps,
+           "speedup_fused_vs_same_kernel_1gpu": dt_single / dt_fused,
+           "fused_pose_equals_1gpu_kernel": bool(np.array_equal(fpose, ref[0])),
+           "nccl_pose_equals_1gpu_kernel": bool(np.array_equal(pose, ref[0])),
+           "collective": ("none (1 rank)" if world == 1 else
+                          "fused: peer-mailbox all-reduce of 32 fp64 inside the kernel; "
+                          "nccl: NCCL all-reduce of 32 fp64 per sweep")}
     if rank == 0 and args.check:
         from oracle import uw_oracle as O
+        prev, cur = pair[0].cpu().numpy(), pair[1].cpu().numpy()
         p = O.default_params(*synth.CALIB[calib])
         op, _, _ = O.estimate_pose(p, O.FrameData(prev), O.FrameData(cur, with_candidates=False))
-        res["pose_bit_identical_to_oracle"] = bool(np.array_equal(op, pose))
+        res["pose_bit_identical_to_oracle"] = bool(np.array_equal(op, fpose))
+    t.close()
     return res
 
 

@@ -93,6 +93,11 @@ struct uwt_tracker {
   size_t flow_ws_bytes = 0;
   int* h_flow_ctl = nullptr;          // pinned copy of its control block {head, tail, active, error}
   bool flow_last = false;
+  void* d_scratch = nullptr;          // grow-only scratch of the read-back accessors
+  size_t scratch_bytes = 0;
+  int flow_grid = 0;                  // persistent grid of the dataflow kernel (0 = not computed)
+  int sm_count = 148;
+  bool last_traced = false;           // the last estimate filled d_trace / d_trace_count
   float* d_out_poses = nullptr;
   uwt_track_stats* d_stats = nullptr;
   float* h_out_poses = nullptr;       // pinned
@@ -135,6 +140,22 @@ int fail(uwt_tracker* t, int code, const char* fmt, ...) {
   } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Grow-only device scratch for the accessors that are not on the hot path (uwt_warp_points,
+// uwt_get_gradients): no cudaMalloc / cudaFree per call.  Calls on a handle are serialised by
+// the caller and every user synchronises the stream before it returns.
+void* scratch(uwt_tracker* t, size_t bytes) {
+  if (bytes > t->scratch_bytes) {
+    cudaStreamSynchronize(t->stream);
+    cudaFree(t->d_scratch);
+    t->d_scratch = nullptr;
+    t->scratch_bytes = 0;
+    const size_t want = align_up(bytes, (size_t)1 << 20);
+    if (cudaMalloc(&t->d_scratch, want) != cudaSuccess) return nullptr;
+    t->scratch_bytes = want;
+  }
+  return t->d_scratch;
+}
 
 cudaEvent_t prof_event(uwt_tracker* t) {
   if (t->ev_used == t->ev_pool.size()) {
@@ -309,6 +330,7 @@ void destroy_impl(uwt_tracker* t) {
   if (t->h_shard_done) cudaFreeHost(t->h_shard_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   cudaFree(t->d_flow_ws);
+  cudaFree(t->d_scratch);
   if (t->h_flow_ctl) cudaFreeHost(t->h_flow_ctl);
   cudaFree(t->d_out_poses);
   cudaFree(t->d_stats);
@@ -511,6 +533,7 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
       return UWT_E_CUDA;
     }
     if (prop.major >= 10) t->max_cluster = 16;
+    if (prop.multiProcessorCount > 0) t->sm_count = prop.multiProcessorCount;
   }
   CREATE_CUDA(cudaStreamSynchronize(t->stream));
 #undef CREATE_CUDA
@@ -866,24 +889,31 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
         UWT_CUDA(t, cudaStreamSynchronize(t->stream));
       }
       ProfSpan span(t, UWT_K_ESTIMATE);
+      // one persistent CTA per SM (cooperative launch: all of them must be co-resident)
       const int k = launch_shard_fused(t->geom, t->pools, t->d_shard, t->d_fused_self,
-                                       t->d_mailbox_self, t->d_shard_partials, 148, t->stream);
-      if (k < 0) return fail(t, UWT_E_CUDA, "fused estimate kernel launch failed: %s",
-                             cudaGetErrorString(cudaGetLastError()));
-      t->launches += k;
-      span.done(k);
-      UWT_CUDA(t, cudaMemcpyAsync(t->h_out_poses, reinterpret_cast<char*>(t->d_shard) +
-                                  offsetof(ShardState, pose), sizeof(float) * 7,
-                                  cudaMemcpyDeviceToHost, t->stream));
-      UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, reinterpret_cast<char*>(t->d_shard) +
-                                  offsetof(ShardState, stats), sizeof(uwt_track_stats),
-                                  cudaMemcpyDeviceToHost, t->stream));
-      UWT_CUDA(t, cudaEventRecord(t->poses_ready, t->stream));
+                                       t->d_mailbox_self, t->d_shard_partials,
+                                       std::min(t->sm_count, kShardMaxGrid), t->stream);
+      if (k >= 0) {
+        t->launches += k;
+        span.done(k);
+        UWT_CUDA(t, cudaMemcpyAsync(t->h_out_poses, reinterpret_cast<char*>(t->d_shard) +
+                                    offsetof(ShardState, pose), sizeof(float) * 7,
+                                    cudaMemcpyDeviceToHost, t->stream));
+        UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, reinterpret_cast<char*>(t->d_shard) +
+                                    offsetof(ShardState, stats), sizeof(uwt_track_stats),
+                                    cudaMemcpyDeviceToHost, t->stream));
+        UWT_CUDA(t, cudaEventRecord(t->poses_ready, t->stream));
+        if ((rc = release(t, r))) return rc;
+        t->last_n = 1;
+        t->shard_active = false;
+        t->flow_last = false;
+        t->last_traced = false;
+        return UWT_OK;
+      }
+      // the cooperative launch was refused (fewer co-resident CTAs, shared memory): clear the
+      // error and let the cluster kernel below serve the problem
+      cudaGetLastError();
       if ((rc = release(t, r))) return rc;
-      t->last_n = 1;
-      t->shard_active = false;
-      t->flow_last = false;
-      return UWT_OK;
     }
   }
   ArgRegion* r = nullptr;
@@ -927,9 +957,17 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   ProfSpan span(t, UWT_K_ESTIMATE);
   const int variant = (t->cfg.flags & UWT_FLAG_DMMA_ACCUM) ? UWT_EST_MMA : UWT_EST_REGISTERS;
   int k = -2;
-  if (use_flow) k = launch_estimate_flow(t->geom, t->pools, n, io, t->d_flow_ws, t->stream);
+  bool flow_used = false;
+  if (use_flow) {
+    k = launch_estimate_flow(t->geom, t->pools, n, io, t->d_flow_ws, t->stream, &t->flow_grid);
+    flow_used = k > 0;
+    if (k < 0) {  // not launchable here (task-word limits, shared memory): the cluster kernel can
+      cudaGetLastError();
+      k = -2;
+    }
+  }
   if (k == -2) k = launch_estimate(t->geom, t->pools, n, io, cluster, t->stream, variant);
-  while (k < 0 && cluster > 1 && !use_flow) {  // a 16-CTA cluster may not be schedulable on every part
+  while (k < 0 && cluster > 1 && !flow_used) {  // a 16-CTA cluster may not be schedulable on every part
     cudaGetLastError();
     cluster /= 2;
     t->max_cluster = cluster;
@@ -943,7 +981,8 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
                               cudaMemcpyDeviceToHost, t->stream));
   UWT_CUDA(t, cudaMemcpyAsync(t->h_stats, t->d_stats, sizeof(uwt_track_stats) * n,
                               cudaMemcpyDeviceToHost, t->stream));
-  t->flow_last = use_flow && k > 0;
+  t->flow_last = flow_used;
+  t->last_traced = tracing;
   if (t->flow_last)
     UWT_CUDA(t, cudaMemcpyAsync(t->h_flow_ctl, t->d_flow_ws, sizeof(int) * 4,
                                 cudaMemcpyDeviceToHost, t->stream));
@@ -1166,21 +1205,23 @@ int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7
     return fail(t, UWT_E_INVALID, "bad argument to uwt_warp_points");
   if (n == 0) return UWT_OK;
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  float *d_pts = nullptr, *d_out = nullptr, *d_pose = nullptr;
-  UWT_CUDA(t, cudaMalloc(&d_pts, sizeof(float) * 4 * n));
-  UWT_CUDA(t, cudaMalloc(&d_out, sizeof(float) * 4 * n));
-  UWT_CUDA(t, cudaMalloc(&d_pose, sizeof(float) * 7));
-  cudaMemcpyAsync(d_pts, pts4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, t->stream);
-  cudaMemcpyAsync(d_pose, pose7, sizeof(float) * 7, cudaMemcpyHostToDevice, t->stream);
+  const size_t pts_bytes = align_up(sizeof(float) * 4 * (size_t)n, 256);
+  char* base = static_cast<char*>(scratch(t, 2 * pts_bytes + 256));
+  if (!base) return fail(t, UWT_E_NOMEM, "out of device memory for %d points", n);
+  float* d_pts = reinterpret_cast<float*>(base);
+  float* d_out = reinterpret_cast<float*>(base + pts_bytes);
+  float* d_pose = reinterpret_cast<float*>(base + 2 * pts_bytes);
+  UWT_CUDA(t, cudaMemcpyAsync(d_pts, pts4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice,
+                              t->stream));
+  UWT_CUDA(t, cudaMemcpyAsync(d_pose, pose7, sizeof(float) * 7, cudaMemcpyHostToDevice,
+                              t->stream));
   const int k = launch_warp_points(t->geom, d_pts, n, d_pose, level, d_out, t->stream);
-  if (k > 0) t->launches += k;
-  cudaMemcpyAsync(out4, d_out, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, t->stream);
-  cudaError_t e = cudaStreamSynchronize(t->stream);
-  cudaFree(d_pts);
-  cudaFree(d_out);
-  cudaFree(d_pose);
-  if (k < 0 || e != cudaSuccess)
-    return fail(t, UWT_E_CUDA, "warp kernel failed: %s", cudaGetErrorString(e));
+  if (k < 0) return fail(t, UWT_E_CUDA, "warp kernel launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+  t->launches += k;
+  UWT_CUDA(t, cudaMemcpyAsync(out4, d_out, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost,
+                              t->stream));
+  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
   return UWT_OK;
 }
 
@@ -1246,27 +1287,24 @@ int uwt_get_gradients(uwt_tracker* t, int slot, int level, int16_t* gx, int16_t*
   if (gx || gy) {
     // gradientX_/gradientY_ planes are not kept on the device (the tracker consumes packed
     // records): materialise them for this slot with the same kernel and copy the level out
-    int16_t* tmp = nullptr;
     const size_t pe = t->geom.plane_elems;
-    UWT_CUDA(t, cudaMalloc(&tmp, 2 * pe * sizeof(int16_t)));
+    int16_t* tmp = static_cast<int16_t*>(scratch(t, 2 * pe * sizeof(int16_t)));
+    if (!tmp) return fail(t, UWT_E_NOMEM, "out of device memory for the gradient planes");
     ArgRegion* r = nullptr;
-    if ((rc = acquire(t, &r))) { cudaFree(tmp); return rc; }
-    if ((rc = push_slots(t, r, 1, &slot, nullptr))) { cudaFree(tmp); return rc; }
+    if ((rc = acquire(t, &r))) return rc;
+    if ((rc = push_slots(t, r, 1, &slot, nullptr))) return rc;
     const int k = launch_gradient(t->geom, t->pools, 1, r->d_int, t->stream,
                                   level_range(t->geom, 0, t->geom.levels - 1), tmp, tmp + pe);
-    if (k > 0) t->launches += k;
-    release(t, r);
-    cudaError_t e = cudaSuccess;
+    if (k < 0) return fail(t, UWT_E_CUDA, "gradient kernel launch failed: %s",
+                           cudaGetErrorString(cudaGetLastError()));
+    t->launches += k;
+    if ((rc = release(t, r))) return rc;
     if (gx)
-      e = cudaMemcpy2DAsync(gx, L.w * 2, tmp + L.plane_off, L.pitch * 2, L.w * 2, L.h,
-                            cudaMemcpyDeviceToHost, t->stream);
-    if (gy && e == cudaSuccess)
-      e = cudaMemcpy2DAsync(gy, L.w * 2, tmp + pe + L.plane_off, L.pitch * 2, L.w * 2, L.h,
-                            cudaMemcpyDeviceToHost, t->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
-    cudaFree(tmp);
-    if (k < 0 || e != cudaSuccess)
-      return fail(t, UWT_E_CUDA, "gradient read-back failed: %s", cudaGetErrorString(e));
+      UWT_CUDA(t, cudaMemcpy2DAsync(gx, L.w * 2, tmp + L.plane_off, L.pitch * 2, L.w * 2, L.h,
+                                    cudaMemcpyDeviceToHost, t->stream));
+    if (gy)
+      UWT_CUDA(t, cudaMemcpy2DAsync(gy, L.w * 2, tmp + pe + L.plane_off, L.pitch * 2, L.w * 2, L.h,
+                                    cudaMemcpyDeviceToHost, t->stream));
   }
   if (g)
     UWT_CUDA(t, cudaMemcpy2DAsync(g, L.w, t->pools.g + off, L.pitch, L.w, L.h,
@@ -1382,6 +1420,9 @@ int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, 
   if (!t->d_trace) return fail(t, UWT_E_STATE, "tracker was not created with UWT_FLAG_TRACE");
   if (index < 0 || index >= t->last_n || index >= kTraceProblems || !out || !n)
     return fail(t, UWT_E_INVALID, "bad trace index %d", index);
+  if (!t->last_traced)
+    return fail(t, UWT_E_STATE, "the last estimate was not traced (UWT_FLAG_TRACE records batches "
+                "of at most %d problems, and not the single-large-frame path)", kTraceProblems);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   int cnt = 0;
   UWT_CUDA(t, cudaMemcpyAsync(&cnt, t->d_trace_count + index, sizeof(int), cudaMemcpyDeviceToHost,

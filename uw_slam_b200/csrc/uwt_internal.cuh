@@ -206,8 +206,9 @@ size_t flow_workspace_bytes(const Geom& g, int nprob);
 #ifdef UWT_FLOW_STATS
 void flow_debug_dump();
 #endif
+// `grid_cache`: per-handle storage of the persistent grid size (0 = not computed yet)
 int launch_estimate_flow(const Geom& g, const Pools& p, int n, const EstimateIO& io,
-                         void* workspace, cudaStream_t st);
+                         void* workspace, cudaStream_t st, int* grid_cache);
 int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, double* partials,
                             double* out32, int grid, cudaStream_t stream);
 int launch_shard_update(const Geom& g, const Pools& p, ShardState* st, const double* sums32,

@@ -137,3 +137,40 @@ def render_batch_torch(calib_name, seeds, device, rot=5e-3, trans=5e-3, dtype=No
         qy = (Hi[1, 0] * xs + Hi[1, 1] * ys + Hi[1, 2]) / d
         cur[b] = ev(qx, qy, tp)
     return prev, cur
+
+
+def render_pairs_torch(calib_name, seeds, device, rot=5e-3, trans=5e-3, chunk=32):
+    """render_batch_torch vectorised over chunks of seeds (float32): fills thousands of pairs
+    in a second on a GPU.  Returns two u8 tensors [B,H,W] on `device` (prev, cur)."""
+    import torch
+
+    calib = CALIB[calib_name] if isinstance(calib_name, str) else calib_name
+    w, h = calib[0], calib[1]
+    B = len(seeds)
+    prev = torch.empty((B, h, w), dtype=torch.uint8, device=device)
+    cur = torch.empty_like(prev)
+    ys, xs = torch.meshgrid(torch.arange(h, device=device, dtype=torch.float32),
+                            torch.arange(w, device=device, dtype=torch.float32), indexing="ij")
+
+    def ev(px, py, kx, ky, amp, ph):
+        v = torch.zeros_like(px)
+        for k in range(N_WAVES):
+            v += amp[:, k] * torch.sin(kx[:, k] * px + ky[:, k] * py + ph[:, k])
+        return torch.clamp(torch.round(127.5 + v), 0, 255).to(torch.uint8)
+
+    for b0 in range(0, B, chunk):
+        bs = seeds[b0:b0 + chunk]
+        tps = [texture_params(s) for s in bs]
+        kx, ky, amp, ph = [torch.tensor(np.stack([tp[j] for tp in tps]), device=device,
+                                        dtype=torch.float32)[:, :, None, None] for j in range(4)]
+        Hi = torch.tensor(np.stack([homography_inv(calib, *motion(s, rot, trans)) for s in bs]),
+                          device=device, dtype=torch.float32)
+        one = torch.ones((len(bs), 1, 1), device=device)
+        prev[b0:b0 + len(bs)] = ev(xs * one, ys * one, kx, ky, amp, ph)
+        d = Hi[:, 2, 0, None, None] * xs + Hi[:, 2, 1, None, None] * ys + Hi[:, 2, 2, None, None]
+        qx = (Hi[:, 0, 0, None, None] * xs + Hi[:, 0, 1, None, None] * ys +
+              Hi[:, 0, 2, None, None]) / d
+        qy = (Hi[:, 1, 0, None, None] * xs + Hi[:, 1, 1, None, None] * ys +
+              Hi[:, 1, 2, None, None]) / d
+        cur[b0:b0 + len(bs)] = ev(qx, qy, kx, ky, amp, ph)
+    return prev, cur
