@@ -264,6 +264,16 @@ def run_reference(args):
     B, K, W = args.batch, args.steps, args.warmup
     seeds = list(range(B))
     fr = gen_sequences(torch, dev, seeds, 1 + W + K).cpu().numpy()      # [frames, B, H, W]
+    # the single-thread figure first (the reference is single-threaded): a bounded sample of the
+    # same sequences, same steps, on an otherwise idle host
+    n1 = min(B, args.cpu_sequences_1t)
+    trk1 = CpuTrackers(fr[0][:n1], 1)
+    t1 = 0.0
+    for i in range(1, 1 + W + K):
+        _, dt = trk1.step(fr[i][:n1])
+        if i > W:
+            t1 += dt
+    trk1.close()
     trk = CpuTrackers(fr[0], threads)
     times = []
     for i in range(1, 1 + W + K):
@@ -273,16 +283,6 @@ def run_reference(args):
     trk.close()
     total = sum(times)
     value = B * K / total
-    # the single-thread figure (the reference is single-threaded): a bounded sample of the
-    # same sequences, same steps
-    n1 = min(B, args.cpu_sequences_1t)
-    trk1 = CpuTrackers(fr[0][:n1], 1)
-    t1 = 0.0
-    for i in range(1, 1 + W + K):
-        _, dt = trk1.step(fr[i][:n1])
-        if i > W:
-            t1 += dt
-    trk1.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tracks/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W,

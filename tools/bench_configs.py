@@ -139,6 +139,7 @@ def batch8192(args, torch, dist, rank, local_rank, world):
         prev[a:b], cur[a:b] = p_, c_
     ps, cs = list(range(chunk)), list(range(chunk, 2 * chunk))
     out = np.empty((mine, 7), np.float32)
+    torch.cuda.synchronize()   # torch's streams are not ordered with the library's stream
 
     def run():
         for a in range(0, mine, chunk):
@@ -251,6 +252,7 @@ def shard4k(args, torch, dist, rank, local_rank, world):
         pair[0], pair[1] = p_[0], c_[0]
     if world > 1:
         dist.broadcast(pair, src=0)
+    torch.cuda.synchronize()   # torch's streams are not ordered with the library's stream
     t = make_tracker(calib, local_rank, max_frames=2)
     t.AddFramesDevice([0, 1], pair.data_ptr())
     t.ApplyGradient([0])
