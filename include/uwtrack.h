@@ -110,6 +110,11 @@ extern "C" {
  * materialised by the same kernels when a read-back accessor asks for them.  Every result is
  * identical to the default (eager) mode, which does what the reference does on all levels. */
 #define UWT_FLAG_LAZY_LEVELS 8u
+/* A/B switch: keep the pyramid (uwt_upload_frames) and the gradient images (uwt_apply_gradient)
+ * in separate kernels.  By default a freshly uploaded frame gets its pyramid AND the gradient
+ * images of all levels from one fused kernel (one read of the frame, staged by a 2-D tensor
+ * copy), and uwt_apply_gradient has nothing left to launch for it; results are identical. */
+#define UWT_FLAG_SEPARATE_GRADIENT 16u
 
 typedef struct uwt_tracker uwt_tracker;
 

@@ -367,9 +367,9 @@ def test_batch_of_independent_pairs(oracle, pairs):
         rp, rc = oracle.FrameData(prevs[s]), oracle.FrameData(curs[s], with_candidates=False)
         opose, _, _ = oracle.estimate_pose(p, rp, rc)
         assert np.array_equal(poses[s], opose), s
-    # uploads 2, gradient 1, candidates 4 (count, scan, scatter, bitmask), estimate 2 (ring init +
-    # dataflow kernel)
-    assert t.launch_count() == 2 + 1 + 4 + 2
+    # uploads 2 (fused pyramid + gradient kernel: ApplyGradient has nothing left to launch),
+    # candidates 4 (count, scan, scatter, bitmask), estimate 2 (ring init + dataflow kernel)
+    assert t.launch_count() == 2 + 0 + 4 + 2
     t.close()
 
 

@@ -15,6 +15,7 @@ FLAG_TRACE = 1
 FLAG_DMMA_ACCUM = 2
 FLAG_CLUSTER_KERNEL = 4
 FLAG_LAZY_LEVELS = 8
+FLAG_SEPARATE_GRADIENT = 16
 WEIGHT_IDENTITY, WEIGHT_TUKEY, WEIGHT_HUBER = 0, 1, 2
 DEPTH_NONE, DEPTH_REFERENCE, DEPTH_U16, DEPTH_ALL_POINTS = 0, 1, 2, 3
 GRADIENT_SCHARR, GRADIENT_SOBEL = 0, 1

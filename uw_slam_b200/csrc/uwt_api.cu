@@ -5,6 +5,7 @@
 // of pinned argument buffers, and enqueues the kernels of the hot path on one stream.
 // There is no CPU fallback anywhere in this file: without a usable CUDA device every entry
 // point returns UWT_E_CUDA.
+#include <cmath>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -195,6 +196,10 @@ int build_geom(const uwt_config& c, Geom& g) {
   g.max_iterations = c.max_iterations;
   g.epsilon = c.epsilon;
   g.residual_scale = c.residual_scale;
+  g.residual_scale_is_int =
+      (c.residual_scale == std::trunc(c.residual_scale) && std::fabs(c.residual_scale) <= 32768.0f)
+          ? 1 : 0;
+  g.residual_scale_int = g.residual_scale_is_int ? (int)c.residual_scale : 0;
   g.gradient_threshold = c.gradient_threshold;
   g.solve_mode = c.solve_mode;
   g.lm_lambda = c.lm_lambda;
@@ -220,6 +225,8 @@ int build_geom(const uwt_config& c, Geom& g) {
     L.w = c.width >> l;
     L.h = c.height >> l;
     L.pitch = (int)align_up((size_t)L.w, 16);
+    L.wf = (float)L.w; L.hf = (float)L.h;
+    L.wm1 = L.w - 1; L.hm1 = L.h - 1;
     L.fx = fx[l]; L.fy = fy[l]; L.cx = cx[l]; L.cy = cy[l];
     L.invfx = 1 / fx[l];
     L.invfy = 1 / fy[l];
@@ -246,6 +253,9 @@ int build_geom(const uwt_config& c, Geom& g) {
     tiles += L.tiles_x * L.tiles_y;
     items += L.nstrip * L.nseg;
   }
+  for (int l = c.last_level; l <= c.first_level; ++l)
+    if (std::fabs(g.lv[l].cx) < 0.00390625f || std::fabs(g.lv[l].cy) < 0.00390625f)
+      g.exact_div = 1;
   g.plane_elems = plane;
   g.mask_elems = mask ? mask : 64;
   g.mask_words_total = (int)mask;
@@ -299,7 +309,7 @@ void destroy_impl(uwt_tracker* t) {
   if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   if (t->stream) cudaStreamSynchronize(t->stream);
   Pools& p = t->pools;
-  cudaFree(p.img); cudaFree(p.g); cudaFree(p.gpart);
+  cudaFree(p.img); cudaFree(p.g); cudaFree(p.gpart); cudaFree(p.gsum);
   cudaFree(p.ticket); cudaFree(p.ithr); cudaFree(p.cnt); cudaFree(p.ncand);
   cudaFree(p.sel_mask); cudaFree(p.rec); cudaFree(p.dep); cudaFree(p.recz);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
@@ -463,6 +473,8 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
   CREATE_CUDA(cudaMalloc(&p.g, F * g.plane_elems));
   CREATE_CUDA(cudaMalloc(&p.gpart, F * g.tile_elems * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.ticket, F * kMaxLevels * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMalloc(&p.gsum, F * kMaxLevels * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemsetAsync(p.gsum, 0, F * kMaxLevels * sizeof(unsigned long long), t->stream));
   CREATE_CUDA(cudaMalloc(&p.ithr, F * kMaxLevels * sizeof(int)));
   CREATE_CUDA(cudaMalloc(&p.cnt, F * g.cnt_elems * sizeof(uint32_t)));
   CREATE_CUDA(cudaMalloc(&p.ncand, F * kMaxLevels * sizeof(uint32_t)));
@@ -607,8 +619,20 @@ static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t
   rc = push_slots(t, r, n, slots, nullptr);
   if (rc) return rc;
   ProfSpan span(t, UWT_K_PYRAMID);
-  const int k = launch_pyramid(t->geom, t->pools, n, r->d_int, dev_src, row_stride, frame_stride,
-                               false, t->stream, t->remap);
+  // Default: pyramid AND gradient images of all levels in one kernel (one read of the frame,
+  // staged by a 2-D tensor copy); uwt_apply_gradient then has nothing left to do for these
+  // slots.  The separate kernels serve what the fused one does not: the undistortion front-end,
+  // more than 5 levels, UWT_FLAG_LAZY_LEVELS / UWT_FLAG_SEPARATE_GRADIENT, unaligned sources.
+  int k = -2;
+  bool fused = false;
+  if (!t->remap.map1 && !(t->cfg.flags & (UWT_FLAG_LAZY_LEVELS | UWT_FLAG_SEPARATE_GRADIENT))) {
+    k = launch_frame_fused(t->geom, t->pools, n, r->d_int, dev_src, row_stride, frame_stride,
+                           t->stream);
+    fused = k > 0;
+  }
+  if (k == -2)
+    k = launch_pyramid(t->geom, t->pools, n, r->d_int, dev_src, row_stride, frame_stride, false,
+                       t->stream, t->remap);
   span.done(k);
   if (k < 0) return fail(t, UWT_E_CUDA, "pyramid kernel launch failed: %s",
                          cudaGetErrorString(cudaGetLastError()));
@@ -618,7 +642,8 @@ static int pyramid_common(uwt_tracker* t, int n, const int* slots, const uint8_t
   for (int i = 0; i < n; ++i) {
     SlotState& s = t->slots[slots[i]];
     s.pyramid = true;
-    s.gradient = s.candidates = s.gradient_all = s.candidates_all = s.depth = false;
+    s.gradient = s.gradient_all = fused;
+    s.candidates = s.candidates_all = s.depth = false;
   }
   return UWT_OK;
 }
@@ -781,6 +806,12 @@ int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots) {
   for (int i = 0; i < n; ++i)
     if (!t->slots[slots[i]].pyramid)
       return fail(t, UWT_E_STATE, "slot %d has no frame", slots[i]);
+  // the fused frame kernel has already produced the gradient images of freshly uploaded slots
+  {
+    bool have = true;
+    for (int i = 0; i < n; ++i) have = have && t->slots[slots[i]].gradient_all;
+    if (have) return UWT_OK;
+  }
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
   ArgRegion* r = nullptr;
   if ((rc = acquire(t, &r))) return rc;

@@ -19,6 +19,7 @@
 //             I1 and the Scharr gx, gy of a selected pixel come from an image tile with a
 //             one-pixel halo in shared memory (no int16 gradient planes are read).
 #include <algorithm>
+#include <mutex>
 
 #include "uwt_internal.cuh"
 
@@ -434,8 +435,11 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   // persistent grids: a multiple of the 148 SMs, as many CTAs per SM as the double-buffered
   // tiles allow; small jobs get one CTA per work item
   const long long total = (long long)lr.item_count * n;
-  static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;  // same for every device of a box
-  if (!sms) {
+  // same for every device of a box; computed once, published together (handles may be driven
+  // from different host threads)
+  static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;
+  static std::once_flag occupancy_once;
+  std::call_once(occupancy_once, [] {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -445,7 +449,7 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
     if (sms <= 0) sms = 148;
     if (per_sm_count <= 0) per_sm_count = 4;
     if (per_sm_scatter <= 0) per_sm_scatter = 4;
-  }
+  });
   const int grid_count = (int)std::min<long long>(total, (long long)sms * per_sm_count);
   const int grid_scatter = (int)std::min<long long>(total, (long long)sms * per_sm_scatter);
   const bool depth = g.depth_mode != UWT_DEPTH_NONE;

@@ -45,6 +45,8 @@ struct LevelGeom {
   int tiles_x, tiles_y;
   int tile_off;        // offset inside a slot's per-tile gradient partial sums
   float fx, fy, cx, cy, invfx, invfy;
+  float wf, hf;        // (float)w, (float)h: bounds of the validity test (Tracker.cpp:450)
+  int wm1, hm1;        // w - 1, h - 1: clamp of the nearest-pixel index (ARITHMETIC.md U1)
 };
 
 struct Geom {
@@ -59,6 +61,9 @@ struct Geom {
   int depth_mode;     // UWT_DEPTH_*
   int gradient_op;    // UWT_GRADIENT_*
   int sampling;       // UWT_SAMPLE_*
+  int residual_scale_int, residual_scale_is_int;  // residual_scale as an integer, if it is one
+  int exact_div;      // 1: a principal point of an optimised level is (nearly) 0 -> the residual
+                      // sweep uses the generic IEEE division for every point (uwt_estimate.cu)
   // per-slot strides (elements)
   size_t plane_elems, mask_elems, rec_elems, cnt_elems, tile_elems;
   int mask_words_total;  // bitmask words per slot over the levels without records
@@ -72,6 +77,7 @@ struct Pools {
   uint8_t* g;           // [slot][plane_elems]
   uint32_t* gpart;      // [slot][tile_elems]   per-tile sums of g
   uint32_t* ticket;     // [slot][levels]       last-block tickets (self-resetting)
+  unsigned long long* gsum;  // [slot][kMaxLevels] sums of g per level (fused frame kernel; self-resetting)
   int* ithr;            // [slot][kMaxLevels]   integer threshold per level
   uint32_t* cnt;        // [slot][cnt_elems]    counts, then exclusive offsets
   uint32_t* ncand;      // [slot][kMaxLevels]
@@ -189,6 +195,12 @@ inline LevelRange level_range(const Geom& g, int lo, int hi) {
 int launch_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots, const uint8_t* src,
                    size_t row_stride, size_t frame_stride, bool src_is_slot, cudaStream_t st,
                    const RemapArgs& rm = RemapArgs());
+// K1+K2 fused (pyramid + gradient images of all levels from one tensor-copy-staged read of the
+// frame); -2 = this source / configuration needs the separate kernels
+bool frame_fused_supported(const Geom& g);
+int launch_frame_fused(const Geom& g, const Pools& p, int n, const int* d_slots,
+                       const uint8_t* src, size_t row_stride, size_t frame_stride,
+                       cudaStream_t st);
 int launch_depth_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots,
                          cudaStream_t st);
 int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, const short2* map1,

@@ -445,6 +445,15 @@ class Tracker:
                                                 g.ctypes.data_as(L._u8p)))
         return gx, gy, g
 
+    def get_gradient_image(self, slot, lvl):
+        """gradient_[lvl] exactly as it sits in device memory (no int16 planes requested, so
+        nothing is recomputed for the read-back)."""
+        i = self.level_info(lvl)
+        g = np.empty((i.height, i.width), np.uint8)
+        self._check(self._lib.uwt_get_gradients(self._h, slot, lvl, None, None,
+                                                g.ctypes.data_as(L._u8p)))
+        return g
+
     def get_candidates(self, slot, lvl):
         n = C.c_int(0)
         self._check(self._lib.uwt_get_candidate_count(self._h, slot, lvl, C.byref(n)))
