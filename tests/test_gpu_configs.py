@@ -9,7 +9,7 @@ from uw_slam_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def run_case(oracle, w, h, seed, levels, first, last, batch=1, **cfg):
+def run_case(oracle, w, h, seed, levels, first, last, batch=1, extra_flags=0, **cfg):
     import uw_slam_b200 as U
     import uw_slam_b200._lib as L
     fx, fy, cx, cy = 0.8 * w, 0.82 * w, w / 2 - 0.5, h / 2 - 0.5
@@ -18,7 +18,7 @@ def run_case(oracle, w, h, seed, levels, first, last, batch=1, **cfg):
     t = U.Tracker(False)
     t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
                         max_frames=2 * batch, levels=levels, first_level=first, last_level=last,
-                        flags=L.FLAG_TRACE, **cfg)
+                        flags=L.FLAG_TRACE | extra_flags, **cfg)
     fp = t.AddFrames(list(range(batch)), np.stack([p[0] for p in pairs]))
     fc = t.AddFrames(list(range(batch, 2 * batch)), np.stack([p[1] for p in pairs]))
     t.ApplyGradient(fp)
@@ -80,11 +80,18 @@ def test_parameter_variations(oracle, cfg):
 
 @pytest.mark.parametrize("cfg", [dict(), dict(levels=4, first=3, last=0),
                                  dict(extra=dict(solve_mode=2, lm_lambda=0.2)),
-                                 dict(extra=dict(sampling=1))])   # cluster kernel, batch of 32
+                                 dict(extra=dict(sampling=1)),
+                                 dict(extra=dict(sampling=1, gradient_op=1, solve_mode=2)),
+                                 dict(extra=dict(residual_scale=12.5)),   # generic point loop
+                                 dict(levels=7, first=6, last=3),         # levels beyond 4
+                                 dict(extra=dict(sampling=1), flags=4)])  # 4: cluster kernel
 def test_dataflow_kernel_configurations(oracle, cfg):
-    # 32 problems -> the dataflow kernel; non-default level ranges and the LM/Cholesky solver
-    run_case(oracle, 160, 128, 40, cfg.get("levels", 5), cfg.get("first", 4), cfg.get("last", 1),
-             batch=32, **cfg.get("extra", {}))
+    # 32 problems -> the dataflow kernel (bilinear sampling included); non-default level ranges,
+    # the LM/Cholesky solver, a non-integer residual scale (generic loop), and the same batch
+    # on the cluster kernel for comparison
+    w, h = (320, 256) if cfg.get("levels", 5) > 5 else (160, 128)
+    run_case(oracle, w, h, 40, cfg.get("levels", 5), cfg.get("first", 4), cfg.get("last", 1),
+             batch=32, extra_flags=cfg.get("flags", 0), **cfg.get("extra", {}))
 
 
 @pytest.mark.parametrize("w,h", [(4096, 4096), (4096, 16), (16, 4096), (1936, 1216)])

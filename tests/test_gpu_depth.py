@@ -34,16 +34,19 @@ def test_depth_pyramid_matches_cv2(oracle):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("calib,seed,batch", [("small", 3, 1), ("tum", 1, 1), ("euroc", 2, 1),
-                                              ("small", 10, 30)])
+                                              ("small", 10, 30), ("small", 10, -30)])
 def test_depth_tracking_matches_oracle(oracle, calib, seed, batch, mode):
+    # batch 30: the dataflow kernel's depth mode; batch -30: the same batch on the cluster kernel
     import uw_slam_b200 as U
     import uw_slam_b200._lib as L
+    kernel_flag = L.FLAG_CLUSTER_KERNEL if batch < 0 else 0
+    batch = abs(batch)
     w, h, fx, fy, cx, cy = synth.CALIB[calib]
     pairs = [synth.render_pair(calib, seed + i)[:2] for i in range(batch)]
     deps = [make_depth((h, w), seed + i) for i in range(batch)]
     t = U.Tracker(True, depth_mode=mode)
     t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
-                        max_frames=2 * batch, flags=L.FLAG_TRACE)
+                        max_frames=2 * batch, flags=L.FLAG_TRACE | kernel_flag)
     fp = t.AddFrames(list(range(batch)), np.stack([p[0] for p in pairs]))
     fc = t.AddFrames(list(range(batch, 2 * batch)), np.stack([p[1] for p in pairs]))
     t.ApplyGradient(fp)

@@ -967,12 +967,10 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
   io.trace_cap = t->trace_cap;
   int cluster = pick_cluster(t, n);
   // Batches: the persistent dataflow kernel (chunk tasks, no per-sweep barriers, no tail of
-  // unequal problems), robust weights included.  Few problems, depth, bilinear sampling, the
-  // DMMA A/B variant and an explicit cluster size stay on the cluster kernel.
+  // unequal problems), robust weights, depth input and bilinear sampling included.  Few
+  // problems, the DMMA A/B variant and an explicit cluster size stay on the cluster kernel.
   const bool use_flow = n >= kFlowMinProblems && n < kFlowMaxProblems &&
                         t->cfg.cluster_size == 0 &&
-                        t->cfg.depth_mode == UWT_DEPTH_NONE &&
-                        t->cfg.sampling == UWT_SAMPLE_NEAREST &&
                         !(t->cfg.flags & (UWT_FLAG_DMMA_ACCUM | UWT_FLAG_CLUSTER_KERNEL));
   if (use_flow) {
     const size_t need = flow_workspace_bytes(t->geom, n);
