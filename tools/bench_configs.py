@@ -288,7 +288,23 @@ def shard4k(args, torch, dist, rank, local_rank, world):
     for _ in range(reps):
         ref = t.EstimatePose([0], [1])
     dt_single = (time.perf_counter() - t1) / reps
+    # device time of the kernels alone (CUDA events around the launches): what sharding changes
+    def kernel_ms(fn):
+        t.synchronize()
+        if world > 1:
+            dist.barrier()
+        t.profile(True)
+        for _ in range(10):
+            fn()
+        ms = t.profile_read()["estimate"][0] / 10
+        t.profile(False)
+        return ms
+    k_fused = kernel_ms(lambda: (t.ShardEstimateFusedAsync(0, 1), t.ShardEstimateFusedWait()))
+    k_single = kernel_ms(lambda: t.EstimatePose([0], [1]))
     res = {"metric": "GN pose estimate of one 3840x2160 pair, candidate list sharded over ranks",
+           "kernel_ms_fused_peer_allreduce": k_fused,
+           "kernel_ms_same_fused_kernel_1gpu": k_single,
+           "kernel_speedup_fused_vs_1gpu": k_single / k_fused if k_fused else None,
            "n_gpus": world, "sweeps": sweeps, "points_per_level": list(stats.n_points)[:5],
            "ms_per_estimate_fused_peer_allreduce": 1e3 * dt_fused,
            "us_per_sweep_fused": 1e6 * dt_fused / sweeps,

@@ -96,6 +96,13 @@ struct uwt_tracker {
   bool flow_last = false;
   void* d_scratch = nullptr;          // grow-only scratch of the read-back accessors
   size_t scratch_bytes = 0;
+  ShardState* h_shard_in[4] = {};     // pinned staging of uwt_shard_begin (ring of 4)
+  int h_shard_next = 0;
+  cudaEvent_t h_shard_ev[4] = {};
+  ShardState* h_shard_out = nullptr;  // pinned: state read back after a fused estimate
+  ShardFused* h_fused_out = nullptr;  // pinned: control block (error flag, phase counters)
+  cudaEvent_t fused_done = nullptr;
+  int shard_grid = 0;                 // CTAs of the fused single-problem kernel (0 = all that fit)
   int flow_grid = 0;                  // persistent grid of the dataflow kernel (0 = not computed)
   int sm_count = 148;
   bool last_traced = false;           // the last estimate filled d_trace / d_trace_count
@@ -338,6 +345,13 @@ void destroy_impl(uwt_tracker* t) {
   cudaFree(t->d_shard_partials);
   cudaFree(t->d_shard_done);
   if (t->h_shard_done) cudaFreeHost(t->h_shard_done);
+  for (int i = 0; i < 4; ++i) {
+    if (t->h_shard_in[i]) cudaFreeHost(t->h_shard_in[i]);
+    if (t->h_shard_ev[i]) cudaEventDestroy(t->h_shard_ev[i]);
+  }
+  if (t->h_shard_out) cudaFreeHost(t->h_shard_out);
+  if (t->h_fused_out) cudaFreeHost(t->h_fused_out);
+  if (t->fused_done) cudaEventDestroy(t->fused_done);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   cudaFree(t->d_flow_ws);
   cudaFree(t->d_scratch);
@@ -521,6 +535,13 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
     CREATE_CUDA(cudaMemcpy(t->d_fused_self, &self, sizeof(self), cudaMemcpyHostToDevice));
   }
   CREATE_CUDA(cudaMalloc(&t->d_shard_partials, sizeof(double) * 32 * kShardMaxGrid));
+  for (int i = 0; i < 4; ++i) {
+    CREATE_CUDA(cudaHostAlloc(&t->h_shard_in[i], sizeof(ShardState), cudaHostAllocDefault));
+    CREATE_CUDA(cudaEventCreateWithFlags(&t->h_shard_ev[i], cudaEventDisableTiming));
+  }
+  CREATE_CUDA(cudaHostAlloc(&t->h_shard_out, sizeof(ShardState), cudaHostAllocDefault));
+  CREATE_CUDA(cudaHostAlloc(&t->h_fused_out, sizeof(ShardFused), cudaHostAllocDefault));
+  CREATE_CUDA(cudaEventCreateWithFlags(&t->fused_done, cudaEventDisableTiming));
   CREATE_CUDA(cudaMalloc(&t->d_shard_done, sizeof(int)));
   CREATE_CUDA(cudaHostAlloc(&t->h_shard_done, sizeof(int), cudaHostAllocDefault));
   CREATE_CUDA(cudaMalloc(&t->d_out_poses, sizeof(float) * 7 * F));
@@ -547,6 +568,10 @@ int uwt_create(const uwt_config* cfg, uwt_tracker** out) {
     if (prop.major >= 10) t->max_cluster = 16;
     if (prop.multiProcessorCount > 0) t->sm_count = prop.multiProcessorCount;
   }
+  // one persistent CTA per SM: measured better than two (the leader's reduction over the per-CTA
+  // partials grows with the grid: 0.186 vs 0.197 ms per 3840x2160 estimate)
+  t->shard_grid = std::min(t->sm_count, kShardMaxGrid);
+  if (const char* e = getenv("UWT_SHARD_GRID")) t->shard_grid = atoi(e);
   CREATE_CUDA(cudaStreamSynchronize(t->stream));
 #undef CREATE_CUDA
   *out = t;
@@ -920,10 +945,10 @@ int uwt_estimate_pose_async(uwt_tracker* t, int n, const int* prev_slots, const 
         UWT_CUDA(t, cudaStreamSynchronize(t->stream));
       }
       ProfSpan span(t, UWT_K_ESTIMATE);
-      // one persistent CTA per SM (cooperative launch: all of them must be co-resident)
+      // as many persistent CTAs as the device holds at once (cooperative launch)
       const int k = launch_shard_fused(t->geom, t->pools, t->d_shard, t->d_fused_self,
-                                       t->d_mailbox_self, t->d_shard_partials,
-                                       std::min(t->sm_count, kShardMaxGrid), t->stream);
+                                       t->d_mailbox_self, t->d_shard_partials, t->shard_grid,
+                                       t->stream);
       if (k >= 0) {
         t->launches += k;
         span.done(k);
@@ -1060,7 +1085,11 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
     return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slot);
   if (!t->slots[cur_slot].pyramid) return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slot);
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  ShardState s;
+  // pinned staging (ring of 4, an event per entry): the state travels without a host sync
+  const int si = t->h_shard_next;
+  t->h_shard_next = (si + 1) & 3;
+  UWT_CUDA(t, cudaEventSynchronize(t->h_shard_ev[si]));  // its previous copy has been consumed
+  ShardState& s = *t->h_shard_in[si];
   std::memset(&s, 0, sizeof(s));
   // SE3::exp(0) is exactly the identity (Tracker.cpp:385)
   const float ident[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
@@ -1072,7 +1101,7 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
   s.prev_slot = prev_slot;
   s.cur_slot = cur_slot;
   UWT_CUDA(t, cudaMemcpyAsync(t->d_shard, &s, sizeof(s), cudaMemcpyHostToDevice, t->stream));
-  UWT_CUDA(t, cudaStreamSynchronize(t->stream));  // `s` is a stack object
+  UWT_CUDA(t, cudaEventRecord(t->h_shard_ev[si], t->stream));
   t->shard_active = true;
   return UWT_OK;
 }
@@ -1200,7 +1229,7 @@ int uwt_shard_estimate_fused_async(uwt_tracker* t, int prev_slot, int cur_slot,
     return fail(t, UWT_E_STATE, "call uwt_shard_ipc_connect / uwt_shard_connect_local first");
   int rc = uwt_shard_begin(t, prev_slot, cur_slot, t->fused_rank, t->fused_nranks, init_pose7);
   if (rc) return rc;
-  if (grid <= 0) grid = 148;
+  if (grid <= 0) grid = t->shard_grid;
   if (grid > kShardMaxGrid) grid = kShardMaxGrid;
   ProfSpan span(t, UWT_K_ESTIMATE);
   const int k = launch_shard_fused(t->geom, t->pools, t->d_shard, t->d_fused, t->d_mailbox,
@@ -1209,22 +1238,32 @@ int uwt_shard_estimate_fused_async(uwt_tracker* t, int prev_slot, int cur_slot,
                          cudaGetErrorString(cudaGetLastError()));
   t->launches += k;
   span.done(k);
+  // result and control block follow the kernel into pinned memory: the wait is ONE event
+  UWT_CUDA(t, cudaMemcpyAsync(t->h_shard_out, t->d_shard, sizeof(ShardState),
+                              cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaMemcpyAsync(t->h_fused_out, t->d_fused, sizeof(ShardFused),
+                              cudaMemcpyDeviceToHost, t->stream));
+  UWT_CUDA(t, cudaEventRecord(t->fused_done, t->stream));
   return UWT_OK;
 }
 
 int uwt_shard_estimate_fused_wait(uwt_tracker* t, float* out_pose7, uwt_track_stats* stats) {
   if (!t) return UWT_E_INVALID;
+  if (!t->shard_active) return fail(t, UWT_E_STATE, "call uwt_shard_estimate_fused_async first");
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  UWT_CUDA(t, cudaStreamSynchronize(t->stream));
-  ShardFused f;
-  UWT_CUDA(t, cudaMemcpy(&f, t->d_fused, sizeof(f), cudaMemcpyDeviceToHost));
+  UWT_CUDA(t, cudaEventSynchronize(t->fused_done));
+  const ShardFused& f = *t->h_fused_out;
   if (getenv("UWT_DEBUG") && f.dbg[5])
     fprintf(stderr, "[uwt fused] sweeps %llu | cycles/sweep: own-accumulate %llu, until-all-CTAs %llu, "
             "reduce %llu, mailbox %llu, K5 %llu\n", f.dbg[5], f.dbg[0] / f.dbg[5], f.dbg[1] / f.dbg[5],
             f.dbg[2] / f.dbg[5], f.dbg[3] / f.dbg[5], f.dbg[4] / f.dbg[5]);
   if (f.error)
     return fail(t, UWT_E_CUDA, "fused sharded estimate: a peer did not arrive (bounded wait expired)");
-  return uwt_shard_result(t, out_pose7, stats);
+  const ShardState& r = *t->h_shard_out;
+  if (!r.done) return fail(t, UWT_E_STATE, "sharded estimate has not finished");
+  if (out_pose7) std::memcpy(out_pose7, r.pose, sizeof(r.pose));
+  if (stats) *stats = r.stats;
+  return UWT_OK;
 }
 
 int uwt_warp_points(uwt_tracker* t, const float* pts4, int n, const float* pose7, int level,

@@ -51,31 +51,6 @@ struct FlowCtl {
   int error;        // != 0: a bounded wait expired
 };
 
-__device__ __forceinline__ void build_tables_range(const DPose& pose, const LevelGeom& L,
-                                                   double* tab_x, int table_w, int xlo, int xhi,
-                                                   double* tab_y, int table_h, int tid,
-                                                   int nthreads) {
-  float R[9];
-  quat_to_R(pose.q, R);  // pose.matrix(), se3.hpp:253-268
-  const int ncol = xhi - xlo + 1;
-  for (int i = tid; i < ncol + L.h; i += nthreads) {
-    const bool isx = i < ncol;
-    const int v = isx ? xlo + i : i - ncol;
-    const float P = isx ? __fmul_rn(__fsub_rn((float)v, L.cx), L.invfx)
-                        : __fmul_rn(__fsub_rn((float)v, L.cy), L.invfy);
-    const double Pd = (double)P;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      if (isx) {
-        tab_x[r * table_w + (v - xlo)] = __dmul_rn((double)R[r * 3 + 0], Pd);
-      } else {
-        const double tc = __dadd_rn((double)R[r * 3 + 2], (double)pose.t[r]);
-        tab_y[r * table_h + v] = fma((double)R[r * 3 + 1], Pd, tc);
-      }
-    }
-  }
-}
-
 // Producer side: publish `nchunks` tasks of problem `prob` (warp-collective, after the state of
 // the problem has been written and fenced).
 // Release / acquire building blocks of the task protocol.  A release store or atomic is
@@ -321,67 +296,6 @@ struct FlowRobust {
   float lut_s[512], lut_rs[512], lut_e[512];  // contiguous: loaded as one [3][512] block
 };
 
-// The point loop of one chunk task at pyramid level LVL.  The level is a template parameter so
-// that the per-level constants (intrinsics, image size, pitch) are compile-time offsets into the
-// __grid_constant__ parameter block: they reach the instructions as constant-bank operands instead
-// of being re-fetched per point through a dynamically indexed LDC.
-template <int LVL, bool kWeighted, int kTab>
-__device__ __forceinline__ void flow_sweep_level(const Geom& geom,
-                                                 const uint64_t* __restrict__ recs, int lo, int hi,
-                                                 int tid, uint64_t rec0, uint64_t rec1,
-                                                 uint32_t tabx, uint32_t taby,
-                                                 const double* tab_x_generic,
-                                                 const double* tab_y_generic,
-                                                 const uint8_t* __restrict__ I2, float rscale,
-                                                 double* acc, unsigned& sum_r2, unsigned& n_val,
-                                                 const WeightLut& lut) {
-  const LevelGeom& L = geom.lv[LVL];
-  WarpConst wc;
-  wc.fx = L.fx; wc.fy = L.fy; wc.cx = L.cx; wc.cy = L.cy;
-  wc.cols = L.w; wc.rows = L.h; wc.pitch = L.pitch;
-  wc.colsf = L.wf; wc.rowsf = L.hf;
-  wc.colsm1 = L.wm1; wc.rowsm1 = L.hm1;
-  // Tracker.cpp:559: residual * 50; the integer scale is a constant-bank operand
-  const int rscale_i = geom.residual_scale_int;
-  static_assert(kFlowChunk <= 32 * kFlowThreads, "one deferred bit per iteration of a thread");
-  // Software pipeline over this thread's stride walk: while point i is accumulated, the geometry
-  // of point i + 1 is evaluated and its target pixel is already being gathered (and the record of
-  // point i + 2 is in flight), all in one basic block.  ncu: the sweep waits on the gather (long
-  // scoreboard), not on issue slots.  Points are still accumulated in stride order.
-  const uint64_t* __restrict__ p = recs + lo + tid;
-  int left = hi - lo - tid;  // > 0 while this thread's stride walk has records left
-  if (left > 0) {
-    // rec0 / rec1: the first two records of the walk, loaded by the caller before the table
-    // build; an absent record repeats the previous one (valid table columns) and is masked out
-    uint64_t rec_next = rec1;
-    FlowPoint cur = flow_point_geometry<kTab>(wc, rec0, true, tabx, taby, I2);
-    int i2 = __ldg(cur.target);
-    unsigned deferred = 0u, bit = 1u;
-    while (left > 0) {
-      left -= kFlowThreads;
-      p += kFlowThreads;
-      const uint64_t rec_nn = (left > kFlowThreads) ? __ldg(p + kFlowThreads) : rec_next;
-      const FlowPoint nxt = flow_point_geometry<kTab>(wc, rec_next, left > 0, tabx, taby, I2);
-      const int i2n = __ldg(nxt.target);
-      flow_point_accumulate<kWeighted>(wc, cur, i2, rscale_i, acc, sum_r2, n_val, lut);
-      deferred |= cur.deferred ? bit : 0u;
-      bit <<= 1;
-      cur = nxt;
-      i2 = i2n;
-      rec_next = rec_nn;
-    }
-    // points whose Z' left the window of the shared-reciprocal division: the generic path, in
-    // this thread's own iteration order (deterministic)
-    while (deferred) {
-      const int j = __ffs(deferred) - 1;
-      deferred &= deferred - 1u;
-      accumulate_point<kWeighted>(wc, __ldg(&recs[lo + tid + j * kFlowThreads]), tab_x_generic,
-                                  kTab, tab_y_generic, kTab, I2, rscale, true, rscale_i, acc,
-                                  sum_r2, n_val, lut);
-    }
-  }
-}
-
 // kMode: 0 = mono input, nearest sampling (the reference; the fast point loop), 1 = per-point
 // depth (cfg.depth_mode; the rigid transform is 12 doubles instead of the separable tables and a
 // record's integer depth comes from `recz`), 2 = bilinear sampling (north-star option; the
@@ -603,22 +517,16 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     {
       const uint32_t tabx = (uint32_t)__cvta_generic_to_shared(tab_x) - (uint32_t)xlo * 8u;
       const uint32_t taby = (uint32_t)__cvta_generic_to_shared(tab_y);
-#define UWT_FLOW_LEVEL(LVL)                                                                      \
-  case LVL:                                                                                      \
-    flow_sweep_level<LVL, kWeighted, kTab>(geom, recs, lo, hi, tid, rec0, rec1, tabx, taby,      \
-                                           tab_x, tab_y, I2, rscale, acc, sum_r2, n_val, lut);   \
-    break;
       // the fast loop assumes the reference's integer residual scale and principal points away
       // from 0 (Geom::exact_div); anything else, levels beyond 4, depth input and bilinear
       // sampling run the generic loop
-      const int fast_lvl =
-          (kMode != kFlowMono || geom.exact_div || !geom.residual_scale_is_int) ? -1 : lvl;
-      switch (fast_lvl) {  // CTA-uniform
-        UWT_FLOW_LEVEL(0)
-        UWT_FLOW_LEVEL(1)
-        UWT_FLOW_LEVEL(2)
-        UWT_FLOW_LEVEL(3)
-        UWT_FLOW_LEVEL(4)
+      const bool fast = kMode == kFlowMono && fast_sweep_applies(geom, lvl);
+      switch (fast ? 1 : 0) {  // CTA-uniform
+        case 1:
+          fast_sweep<kWeighted, kTab>(geom, lvl, recs, lo + tid, hi, kFlowThreads, rec0, rec1,
+                                      tabx, taby, tab_x, tab_y, I2, rscale, acc, sum_r2, n_val,
+                                      lut);
+          break;
         default: {
           int i = lo + tid;
           uint64_t rec = (i < hi) ? __ldg(&recs[i]) : 0ull;
@@ -638,7 +546,6 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
           }
         }
       }
-#undef UWT_FLOW_LEVEL
     }
     acc[27] = (double)sum_r2;
     acc[28] = (double)n_val;

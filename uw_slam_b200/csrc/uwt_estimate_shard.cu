@@ -163,6 +163,7 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
   __shared__ int is_last;
   __shared__ int s_level, s_done;
   __shared__ float s_pose[7];
+  __shared__ int s_ncand[kMaxLevels];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int rank = st->rank, nranks = st->nranks;
   const float rscale = geom.residual_scale;
@@ -171,15 +172,17 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
   const unsigned gen0 = ctl->generation;             // same value in every CTA at launch
   const unsigned long long seq0 = ctl->seq;
   unsigned local_sweep = 0;
+  // state of the first sweep (published by uwt_shard_begin); later sweeps receive it from the
+  // leader's update through ctl->state_ll
+  if (tid == 0) {
+    s_level = *(volatile int*)&st->level;
+    s_done = *(volatile int*)&st->done;
+    for (int i = 0; i < 7; ++i) s_pose[i] = ((volatile float*)st->pose)[i];
+  }
+  if (tid < kMaxLevels) s_ncand[tid] = (int)pools.ncand[(size_t)st->prev_slot * kMaxLevels + tid];
+  __syncthreads();
 
   for (;;) {
-    // ---- state of this sweep (published by the previous update, or by uwt_shard_begin) ----
-    if (tid == 0) {
-      s_level = *(volatile int*)&st->level;
-      s_done = *(volatile int*)&st->done;
-      for (int i = 0; i < 7; ++i) s_pose[i] = ((volatile float*)st->pose)[i];
-    }
-    __syncthreads();
     if (s_done) break;
     const long long c0 = clock64();
     const int lvl = s_level;
@@ -187,8 +190,12 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
     for (int i = 0; i < 4; ++i) pose.q[i] = s_pose[i];
     for (int i = 0; i < 3; ++i) pose.t[i] = s_pose[4 + i];
     const LevelGeom& L = geom.lv[lvl];
-    const long long n = (long long)pools.ncand[(size_t)st->prev_slot * kMaxLevels + lvl];
+    const long long n = (long long)s_ncand[lvl];
     const int lo = (int)(n * rank / nranks), hi = (int)(n * (rank + 1) / nranks);
+    // this CTA's contiguous part of the rank's range: x-major order keeps it inside a few image
+    // columns, so only those columns of the x table are built (plus all rows of the y table)
+    const int clo = lo + (int)((long long)(hi - lo) * blockIdx.x / gridDim.x);
+    const int chi = lo + (int)((long long)(hi - lo) * (blockIdx.x + 1) / gridDim.x);
     const uint64_t* __restrict__ recs =
         pools.rec + (size_t)st->prev_slot * geom.rec_elems + L.rec_off;
     const uint8_t* __restrict__ I2 =
@@ -197,23 +204,46 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
     wc.fx = L.fx; wc.fy = L.fy; wc.cx = L.cx; wc.cy = L.cy;
     wc.cols = L.w; wc.rows = L.h; wc.pitch = L.pitch;
     wc.colsf = (float)L.w; wc.rowsf = (float)L.h;
-    build_tables(pose, L, tab_x, table_w, tab_y, table_h, tid, kShardThreads);
+    int xlo = 0, xhi = -1;
+    if (chi > clo) {
+      xlo = (int)(__ldg(&recs[clo]) & 0xFFFu);
+      xhi = (int)(__ldg(&recs[chi - 1]) & 0xFFFu);
+    }
+    build_tables_range(pose, L, tab_x, table_w, xlo, xhi, tab_y, table_h, tid, kShardThreads);
     __syncthreads();
     double acc[kNQ];
 #pragma unroll
     for (int i = 0; i < kNQ; ++i) acc[i] = 0.0;
     unsigned sum_r2 = 0, n_val = 0;
     {
-      const int stride = gridDim.x * kShardThreads;
-      int i = lo + blockIdx.x * kShardThreads + tid;
-      uint64_t rec = (i < hi) ? __ldg(&recs[i]) : 0ull;
-      while (i < hi) {
-        const int inext = i + stride;
-        const uint64_t rec_next = (inext < hi) ? __ldg(&recs[inext]) : 0ull;
-        accumulate_point<false>(wc, rec, tab_x, table_w, tab_y, table_h, I2, rscale,
-                                rscale_is_int, rscale_i, acc, sum_r2, n_val, WeightLut{});
-        rec = rec_next;
-        i = inext;
+      const int stride = kShardThreads;
+      const int first = clo + tid;
+      // the fast point loop (software-pipelined gather) where a thread has enough points for its
+      // prologue to pay off; its tables have a compile-time row stride (launch_shard_fused)
+      const bool fast = fast_sweep_applies(geom, lvl) && (chi - clo) >= 8 * stride &&
+                        table_w == table_h && (table_w == 1024 || table_w == 2048);
+      if (fast) {
+        const uint64_t rec0 = (first < chi) ? __ldg(&recs[first]) : 0ull;
+        const uint64_t rec1 = (first + stride < chi) ? __ldg(&recs[first + stride]) : rec0;
+        const uint32_t ax = (uint32_t)__cvta_generic_to_shared(tab_x) - (uint32_t)xlo * 8u;
+        const uint32_t ay = (uint32_t)__cvta_generic_to_shared(tab_y);
+        if (table_w == 1024)
+          fast_sweep<false, 1024>(geom, lvl, recs, first, chi, stride, rec0, rec1, ax, ay,
+                                  tab_x - xlo, tab_y, I2, rscale, acc, sum_r2, n_val, WeightLut{});
+        else
+          fast_sweep<false, 2048>(geom, lvl, recs, first, chi, stride, rec0, rec1, ax, ay,
+                                  tab_x - xlo, tab_y, I2, rscale, acc, sum_r2, n_val, WeightLut{});
+      } else {
+        int i = first;
+        uint64_t rec = (i < chi) ? __ldg(&recs[i]) : 0ull;
+        while (i < chi) {
+          const int inext = i + stride;
+          const uint64_t rec_next = (inext < chi) ? __ldg(&recs[inext]) : 0ull;
+          accumulate_point<false>(wc, rec, tab_x - xlo, table_w, tab_y, table_h, I2, rscale,
+                                  rscale_is_int, rscale_i, acc, sum_r2, n_val, WeightLut{});
+          rec = rec_next;
+          i = inext;
+        }
       }
     }
     acc[27] = (double)sum_r2;
@@ -291,17 +321,23 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
       tot[lane] = t;
       __syncwarp();
       const long long c3 = clock64();
+      // ---- K5 on the totals, warp-collective (6x6 LU one row per lane, SE3 exp with two sincos
+      //      lanes): every lane ends with the same pose; then the level bookkeeping (same as
+      //      shard_update_kernel) by lane 0 ----
+      DPose p2 = pose;
+      float last_error = *(volatile float*)&st->last_error;
+      int k = *(volatile int*)&st->k, lv = lvl;
+      bool brk = false;
+      if (ok) {
+        if (lane == 0) st->stats.n_points[lv] = (int)n;
+        __syncwarp();
+        brk = gn_update(geom, tot, lv, k, p2, last_error, &st->stats, nullptr, lane);
+      }
       if (lane == 0) {
         if (!ok) {
           ctl->error = 1;
           st->done = 1;
         } else {
-          // ---- K5 on the totals, then level bookkeeping (same as shard_update_kernel) ----
-          DPose p2 = pose;
-          float last_error = st->last_error;
-          int k = st->k, lv = lvl;
-          st->stats.n_points[lv] = (int)n;
-          const bool brk = gn_update_serial(geom, tot, lv, k, p2, last_error, &st->stats, nullptr);
           if (brk) {
             if (lv != 0) p2 = se3_scale_level(p2);  // Tracker.cpp:580-590
             --lv;
@@ -323,17 +359,37 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
         ctl->dbg[3] += (unsigned long long)(c3 - c2);
         ctl->dbg[4] += (unsigned long long)(clock64() - c3);
         ctl->dbg[5] += 1;
-        __threadfence();
-        st_release_gpu(&ctl->generation, gen0 + local_sweep + 1);  // release the other CTAs
+        ctl->generation = gen0 + local_sweep + 1;  // read by the next launch only
+      }
+      // ---- publish the next sweep's state to the waiting CTAs: 9 LL words, one per lane ----
+      __syncwarp();
+      if (lane < 9) {
+        unsigned payload;
+        if (lane < 7) payload = __float_as_uint(((volatile float*)st->pose)[lane]);
+        else if (lane == 7) payload = (unsigned)*(volatile int*)&st->level;
+        else payload = (unsigned)*(volatile int*)&st->done;
+        const unsigned long long tagw = (unsigned long long)(gen0 + local_sweep + 1) << 32;
+        *(volatile unsigned long long*)&ctl->state_ll[lane] = tagw | payload;
       }
     }
-    // ---- grid barrier: wait until this sweep's update is published ----
-    if (tid == 0) {
+    // ---- grid barrier + state hand-over in one round trip: poll the LL words of this sweep's
+    //      update (tag = generation), payload = pose, level, done ----
+    if (tid < 9) {
+      const unsigned want = gen0 + local_sweep + 1;
+      const volatile unsigned long long* w = &ctl->state_ll[tid];
+      unsigned long long v;
       long long spins = 0;
-      while ((int)(ld_acquire_gpu(&ctl->generation) - (gen0 + local_sweep + 1)) < 0) {
+      while ((unsigned)((v = *w) >> 32) != want) {
         __nanosleep(poll_ns);
-        if (++spins > 4 * kSpinLimit) break;  // the leader reports the error; just leave
+        if (++spins > 4 * kSpinLimit) {  // the leader reports the error; just leave
+          v = (tid == 8) ? 1ull : 0ull;  // done = 1
+          break;
+        }
       }
+      const unsigned payload = (unsigned)(v & 0xffffffffull);
+      if (tid < 7) s_pose[tid] = __uint_as_float(payload);
+      else if (tid == 7) s_level = (int)payload;
+      else s_done = (int)payload;
     }
     __syncthreads();
     ++local_sweep;
@@ -344,10 +400,22 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
 int launch_shard_fused(const Geom& g, const Pools& p, ShardState* st, ShardFused* ctl,
                        ShardMailbox* mine, double* partials, int grid, cudaStream_t stream) {
   int tw = g.lv[g.last_level].w, th = g.lv[g.last_level].h;
+  // transform tables with the compile-time row stride of the fast sweep where the level fits
+  if (std::max(tw, th) <= 1024) tw = th = 1024;
+  else if (std::max(tw, th) <= 2048) tw = th = 2048;
   const size_t smem = sizeof(double) * 3 * (size_t)(tw + th);
   static size_t smem_cache[kMaxDevices];  // one per kernel instantiation and device
   if (!ensure_dynamic_smem(shard_fused_kernel, smem, smem_cache)) return -1;
-  // cooperative launch: all CTAs must be co-resident (they wait on each other)
+  // cooperative launch: all CTAs must be co-resident (they wait on each other); grid <= 0 asks
+  // for every CTA the device can hold at once (two per SM: twice the warps to hide the point
+  // loop's latency)
+  if (grid <= 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_fused_kernel, kShardThreads, smem);
+    grid = std::max(1, std::min(sms * std::max(per_sm, 1), kShardMaxGrid));
+  }
   static unsigned poll_ns = 0;
   if (poll_ns == 0) {
     const char* e = getenv("UWT_POLL_NS");  // tuning knob of the grid / peer wait loops

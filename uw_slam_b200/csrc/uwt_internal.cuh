@@ -154,6 +154,10 @@ struct ShardFused {
   unsigned int error;            // != 0: a bounded wait expired
   unsigned long long dbg[8];     // leader-phase cycle counters (profiling aid)
   ShardMailbox* peer[kShardMaxRanks];  // peer[r] = rank r's mailbox as mapped in this process
+  // The update's result for the next sweep, broadcast to the waiting CTAs in the same "LL" form as
+  // the mailbox: word i = {32-bit payload | generation << 32}, payload = pose[0..6], level, done.
+  // A CTA learns "the update is published" and the new state in ONE round trip.
+  unsigned long long state_ll[16];
 };
 
 // Undistortion front-end fused into the pyramid kernel's level-0 load (System.cpp:232-235):
