@@ -31,7 +31,6 @@ namespace uwt {
 #endif
 constexpr int kFlowThreads = UWT_FLOW_THREADS;
 constexpr int kFlowChunk = UWT_FLOW_CHUNK;  // candidate records per task
-constexpr unsigned kFlowEmpty = 0xFFFFFFFFu;
 constexpr unsigned kFlowExit = 0xFFFFFFFEu;
 
 struct FlowProblem {  // device-resident state of one problem between tasks
@@ -67,13 +66,19 @@ __device__ __forceinline__ void fence_acq_rel_gpu() {
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-__device__ __forceinline__ void flow_enqueue(FlowCtl* ctl, unsigned* ring, unsigned cap, int prob,
+__device__ __forceinline__ void flow_enqueue(FlowCtl* ctl, unsigned long long* ring, unsigned cap, int prob,
                                              int nchunks, int lane) {
   unsigned base = 0;
   if (lane == 0) base = atomicAdd(&ctl->tail, (unsigned)nchunks);
   base = __shfl_sync(0xffffffffu, base, 0);
   for (int c = lane; c < nchunks; c += 32) {
-    st_release_gpu(&ring[(base + c) % cap], ((unsigned)prob << 12) | (unsigned)c);
+    // slot word = {generation of the ring revolution | task}: a consumer recognises ITS task by
+    // the generation of its ticket, so slots are never reset and nothing can be erased
+    const unsigned idx = base + (unsigned)c;
+    const unsigned long long word =
+        ((unsigned long long)(idx / cap + 1u) << 32) | (((unsigned)prob << 12) | (unsigned)c);
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ring[idx % cap]), "l"(word)
+                 : "memory");
   }
 }
 
@@ -105,17 +110,16 @@ void flow_debug_dump() {
 }
 #endif
 
-__device__ __forceinline__ unsigned flow_pop_raw(FlowCtl* ctl, unsigned* ring, unsigned cap,
-                                                 unsigned& spins) {
-  const unsigned ticket = atomicAdd(&ctl->head, 1u);
-  unsigned* const slot = &ring[ticket % cap];
-  unsigned v;
+__device__ __forceinline__ unsigned flow_ticket(FlowCtl* ctl) { return atomicAdd(&ctl->head, 1u); }
+__device__ __forceinline__ unsigned flow_wait_raw(FlowCtl* ctl, unsigned long long* ring,
+                                                  unsigned cap, unsigned ticket, unsigned& spins) {
+  const volatile unsigned long long* const slot = &ring[ticket % cap];
+  const unsigned want = ticket / cap + 1u;  // generation of this ticket's ring revolution
+  unsigned long long w;
   spins = 0;
-  // poll with plain loads, consume with an exchange: read-and-reset is one atomic step, so a
-  // late reset can never erase a task a producer published one ring revolution later
-  for (;;) {
-    v = *reinterpret_cast<volatile unsigned*>(slot);
-    if (v != kFlowEmpty && (v = atomicExch(slot, kFlowEmpty)) != kFlowEmpty) break;
+  // plain polling loads; the slot is consumed by reading it (no reset: the next revolution's
+  // task carries the next generation)
+  while ((unsigned)((w = *slot) >> 32) != want) {
     if (*reinterpret_cast<volatile int*>(&ctl->active) <= 0) return kFlowExit;
     __nanosleep(64);
     // bounded: a protocol error ends the kernel with an error flag instead of hanging the GPU
@@ -125,14 +129,16 @@ __device__ __forceinline__ unsigned flow_pop_raw(FlowCtl* ctl, unsigned* ring, u
     }
     if ((spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(&ctl->error)) return kFlowExit;
   }
+  const unsigned v = (unsigned)w;
   fence_acq_rel_gpu();  // acquire: the problem state written before the publish is visible
   return v;
 }
-__device__ __forceinline__ unsigned flow_pop(FlowCtl* ctl, unsigned* ring, unsigned cap) {
+__device__ __forceinline__ unsigned flow_wait(FlowCtl* ctl, unsigned long long* ring, unsigned cap,
+                                              unsigned ticket) {
   unsigned spins;
 #ifdef UWT_FLOW_STATS
   const unsigned long long t0 = flow_globaltimer();
-  const unsigned v = flow_pop_raw(ctl, ring, cap, spins);
+  const unsigned v = flow_wait_raw(ctl, ring, cap, ticket, spins);
   const unsigned long long t1 = flow_globaltimer();
   const unsigned b = min(63u, (unsigned)((t1 - g_flow_t0) >> 16));
   if (v == kFlowExit) {
@@ -144,8 +150,11 @@ __device__ __forceinline__ unsigned flow_pop(FlowCtl* ctl, unsigned* ring, unsig
   }
   return v;
 #else
-  return flow_pop_raw(ctl, ring, cap, spins);
+  return flow_wait_raw(ctl, ring, cap, ticket, spins);
 #endif
+}
+__device__ __forceinline__ unsigned flow_pop(FlowCtl* ctl, unsigned long long* ring, unsigned cap) {
+  return flow_wait(ctl, ring, cap, flow_ticket(ctl));
 }
 
 struct FlowShared {
@@ -246,7 +255,7 @@ __device__ __forceinline__ void flow_prefetch_level(const Geom& geom, const Pool
 
 // Publishes the new state of a problem: either its final pose, or its next sweep's tasks.
 __device__ __forceinline__ void flow_commit(const EstimateIO& io, int prob, const FlowProblem& fp,
-                                            bool finished, FlowCtl* ctl, unsigned* ring,
+                                            bool finished, FlowCtl* ctl, unsigned long long* ring,
                                             unsigned cap, FlowProblem* probs, int lane) {
   if (finished) {
     if (lane == 0) {
@@ -265,7 +274,7 @@ __device__ __forceinline__ void flow_commit(const EstimateIO& io, int prob, cons
   }
 }
 
-__global__ void flow_init_kernel(FlowCtl* ctl, unsigned* ring, unsigned cap, int nprob) {
+__global__ void flow_init_kernel(FlowCtl* ctl, unsigned long long* ring, unsigned cap, int nprob) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     ctl->head = 0u;
@@ -276,7 +285,7 @@ __global__ void flow_init_kernel(FlowCtl* ctl, unsigned* ring, unsigned cap, int
     g_flow_t0 = flow_globaltimer();
 #endif
   }
-  for (unsigned j = i; j < cap; j += gridDim.x * blockDim.x) ring[j] = kFlowEmpty;
+  for (unsigned j = i; j < cap; j += gridDim.x * blockDim.x) ring[j] = 0ull;  // generation 0
 }
 
 #ifndef UWT_FLOW_MIN_BLOCKS
@@ -304,7 +313,7 @@ constexpr int kFlowMono = 0, kFlowDepth = 1, kFlowBilinear = 2;
 template <bool kWeighted, int kTab, int kMode = kFlowMono>
 __global__ void __launch_bounds__(kFlowThreads, UWT_FLOW_MIN_BLOCKS)
 estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const EstimateIO io,
-                     int nprob, FlowCtl* ctl, unsigned* ring, unsigned cap, FlowProblem* probs,
+                     int nprob, FlowCtl* ctl, unsigned long long* ring, unsigned cap, FlowProblem* probs,
                      double* partials, int max_chunks, unsigned* robust_hist, float* robust_lut) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FlowShared& sh = *reinterpret_cast<FlowShared*>(smem_raw);
@@ -549,6 +558,10 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     }
     acc[27] = (double)sum_r2;
     acc[28] = (double)n_val;
+    // the ticket of the next task is requested now (its atomic's round trip overlaps the warp
+    // reduction); the wait for the slot happens after the barrier
+    unsigned next_ticket = 0u;
+    if (tid == 32) next_ticket = flow_ticket(ctl);
     const double wtot = warp_reduce32(acc, lane);
     sh.warp_part[wid][lane] = wtot;
     __syncthreads();  // warp_part complete; every thread has read sh.task
@@ -556,7 +569,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     // latency chains (ticket + slot + fence; partial store + fence + counter) run side by side.
     // Warp 0 never waits for warp 1 here, so a pop that has to wait for work -- possibly the
     // work warp 0 is about to publish -- cannot block it.
-    if (tid == 32) sh.task = flow_pop(ctl, ring, cap);
+    if (tid == 32) sh.task = flow_wait(ctl, ring, cap, next_ticket);
     if (wid == 0) {
       double s = 0.0;
 #pragma unroll
@@ -619,7 +632,7 @@ constexpr unsigned kFlowRingSlack = 148 * 8 + 64;  // >= CTAs of the persistent 
 
 size_t flow_workspace_bytes(const Geom& g, int nprob) {
   const size_t mc = (size_t)flow_max_chunks(g, kFlowMinChunk);
-  return 256 + round256(((size_t)nprob * mc + kFlowRingSlack) * sizeof(unsigned)) +
+  return 256 + round256(((size_t)nprob * mc + kFlowRingSlack) * sizeof(unsigned long long)) +
          round256((size_t)nprob * sizeof(FlowProblem)) +
          round256((size_t)nprob * mc * kNQ * sizeof(double)) +
          (g.weight_mode == UWT_WEIGHT_TUKEY ? (size_t)nprob * (512 + 1536) * 4 : 0);
@@ -636,8 +649,8 @@ static int launch_estimate_flow_t(const Geom& g, const Pools& p, int n, const Es
   const unsigned cap = (unsigned)((size_t)n * mc) + kFlowRingSlack;
   unsigned char* w = static_cast<unsigned char*>(workspace);
   FlowCtl* ctl = reinterpret_cast<FlowCtl*>(w);
-  unsigned* ring = reinterpret_cast<unsigned*>(w + 256);
-  size_t off = 256 + round256((size_t)cap * sizeof(unsigned));
+  unsigned long long* ring = reinterpret_cast<unsigned long long*>(w + 256);
+  size_t off = 256 + round256((size_t)cap * sizeof(unsigned long long));
   FlowProblem* probs = reinterpret_cast<FlowProblem*>(w + off);
   off += round256((size_t)n * sizeof(FlowProblem));
   double* partials = reinterpret_cast<double*>(w + off);
