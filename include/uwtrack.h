@@ -93,7 +93,7 @@ extern "C" {
 /* How the target image is sampled at the warped position (src/Tracker.cpp:472). */
 #define UWT_SAMPLE_NEAREST 0  /* image2.at<uchar>(round(y2), round(x2)), the reference            */
 #define UWT_SAMPLE_BILINEAR 1 /* north-star wording: float interpolation of the four neighbours;
-                                 identity weights, mono input, cluster kernel                    */
+                                 identity weights, mono input                                    */
 
 /* cfg.flags */
 #define UWT_FLAG_TRACE 1u /* record a per-iteration trace (uwt_get_trace); debugging/parity */
@@ -228,7 +228,9 @@ int uwt_get_depth(uwt_tracker* t, int slot, int level, uint16_t* host);
 
 /* Tracker::ApplyGradient for n slots: gradient_ (u8) on every pyramid level.  The int16
  * gradientX_ / gradientY_ values reach the tracker through the packed candidate records; the
- * full planes are produced on demand by uwt_get_gradients (same stencil, same integers). */
+ * full planes are produced on demand by uwt_get_gradients (same stencil, same integers).
+ * A slot filled by uwt_upload_frames / uwt_set_frames_device already carries its gradient images
+ * (the fused frame kernel, see UWT_FLAG_SEPARATE_GRADIENT): the call then launches nothing. */
 int uwt_apply_gradient(uwt_tracker* t, int n, const int* slots);
 /* Tracker::ObtainCandidatePoints for n slots (needs gradients): candidatePoints_ on every
  * level, in the reference's x-major order. */
