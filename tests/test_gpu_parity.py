@@ -599,3 +599,40 @@ def test_dataflow_kernel_sparse_candidates(oracle):
         assert_trace_equal(t.get_trace(s), otrace)
         assert np.array_equal(poses[s], opose), s
     t.close()
+
+
+def test_dataflow_traces_at_headline_size(oracle):
+    """The headline configuration itself (1280x1024, 16 chunk tasks per level-1 sweep, identity
+    weights, a batch on the dataflow kernel): every sweep of four problems against the oracle --
+    N_valid, sum r^2, error, A, b, delta, pose -- bit for bit, and every final pose."""
+    import uw_slam_b200._lib as L
+    calib, B = "tum_mono", 24
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    pairs = [synth.render_pair(calib, 300 + i, rot=5e-3 * (0.5 + 0.05 * i),
+                               trans=5e-3 * (1.4 - 0.04 * i))[:2] for i in range(4)]
+    t = make_tracker(calib, max_frames=2 * B, flags=L.FLAG_TRACE)
+    prevs = np.stack([pairs[i % 4][0] for i in range(B)])
+    curs = np.stack([pairs[i % 4][1] for i in range(B)])
+    ps, cs = list(range(B)), list(range(B, 2 * B))
+    t.AddFrames(ps, prevs)
+    t.AddFrames(cs, curs)
+    t.ApplyGradient(ps)
+    t.ObtainCandidatePoints(ps)
+    poses = t.EstimatePose(ps, cs)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for i in range(4):
+        rp, rc = oracle.FrameData(pairs[i][0]), oracle.FrameData(pairs[i][1], with_candidates=False)
+        opose, _, otr = oracle.estimate_pose(p, rp, rc)
+        for j in range(i, B, 4):                      # the same pair in several queue positions
+            assert np.array_equal(poses[j], opose), (i, j)
+        tr = t.get_trace(i)
+        assert len(tr) == len(otr) and len(tr) >= 8
+        assert max(a.n_valid for a in tr) > 8192      # multi-chunk sweeps were exercised
+        for a, b in zip(tr, otr):
+            assert (a.level, a.k, a.n_valid, a.broke, a.sum_r2) == \
+                (b.level, b.k, b.n_valid, b.broke, b.sum_r2), (i, b.level, b.k)
+            for f in ("A", "b", "delta", "pose"):
+                assert np.array_equal(np.array(getattr(a, f)[:]), np.array(getattr(b, f)[:])), \
+                    (i, b.level, b.k, f)
+            assert np.float32(a.error) == np.float32(b.error)
+    t.close()

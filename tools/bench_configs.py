@@ -162,13 +162,19 @@ def batch8192(args, torch, dist, rank, local_rank, world):
     run()
     t.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    # device time per kernel class of one more pass (events; not part of the timed figure)
+    t.profile(True)
+    run()
+    prof = {k: v[0] for k, v in t.profile_read().items()}
+    t.profile(False)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     res = {"metric": "pose-tracks/sec, 8192 independent 640x480 pairs (pyramids x2, gradient, "
                      "candidates, estimate per pair; inputs resident in HBM)",
            "value": total / float(dt.item()), "unit": "tracks/s", "pairs": total,
            "n_gpus": world, "scaling": "strong", "chunk": chunk, "flags": args.flags,
-           "weights": ["identity", "tukey_mad", "huber"][args.weights], "depth_mode": args.depth}
+           "weights": ["identity", "tukey_mad", "huber"][args.weights], "depth_mode": args.depth,
+           "kernel_ms_per_pass_rank0": prof}
     if rank == 0:
         # spot-check 4 pairs against the oracle
         from oracle import uw_oracle as O

@@ -94,6 +94,8 @@ struct uwt_tracker {
   size_t flow_ws_bytes = 0;
   int* h_flow_ctl = nullptr;          // pinned copy of its control block {head, tail, active, error}
   bool flow_last = false;
+  uint8_t* d_depth_stage = nullptr;   // device staging of host depth frames (grow-only)
+  size_t depth_stage_frames = 0;
   void* d_scratch = nullptr;          // grow-only scratch of the read-back accessors
   size_t scratch_bytes = 0;
   ShardState* h_shard_in[4] = {};     // pinned staging of uwt_shard_begin (ring of 4)
@@ -156,6 +158,7 @@ void* scratch(uwt_tracker* t, size_t bytes) {
   if (bytes > t->scratch_bytes) {
     cudaStreamSynchronize(t->stream);
     cudaFree(t->d_scratch);
+  cudaFree(t->d_depth_stage);
     t->d_scratch = nullptr;
     t->scratch_bytes = 0;
     const size_t want = align_up(bytes, (size_t)1 << 20);
@@ -355,6 +358,7 @@ void destroy_impl(uwt_tracker* t) {
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   cudaFree(t->d_flow_ws);
   cudaFree(t->d_scratch);
+  cudaFree(t->d_depth_stage);
   if (t->h_flow_ctl) cudaFreeHost(t->h_flow_ctl);
   cudaFree(t->d_out_poses);
   cudaFree(t->d_stats);
@@ -736,24 +740,57 @@ int uwt_upload_depth_frames(uwt_tracker* t, int n, const int* slots, const uint1
   if (!host || row_stride < w * sizeof(uint16_t))
     return fail(t, UWT_E_INVALID, "host NULL or row_stride < 2 * width bytes");
   UWT_CUDA(t, cudaSetDevice(t->cfg.device));
-  const LevelGeom& L0 = t->geom.lv[0];
-  for (int i = 0; i < n; ++i) {
-    uint16_t* dst = t->pools.dep + (size_t)slots[i] * t->geom.plane_elems + L0.plane_off;
-    UWT_CUDA(t, cudaMemcpy2DAsync(dst, (size_t)L0.pitch * sizeof(uint16_t),
-                                  reinterpret_cast<const uint8_t*>(host) + (size_t)i * frame_stride,
-                                  row_stride, w * sizeof(uint16_t), h, cudaMemcpyDefault,
-                                  t->stream));  // host or device-resident depth frames (UVA)
+  // Frames already in device memory are read in place; host frames go through a device staging
+  // buffer (one strided copy per chunk when the frames are contiguous).  Either way level 0 of
+  // all n slots is written by ONE kernel, then the pyramid kernels run on the slots.
+  cudaPointerAttributes attr;
+  const bool on_device = cudaPointerGetAttributes(&attr, host) == cudaSuccess &&
+                         (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(host);
+  const size_t dense_row = w * sizeof(uint16_t), dense_frame = dense_row * h;
+  const size_t cap = on_device ? (size_t)n
+                               : std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)128 << 20) / dense_frame));
+  if (!on_device && t->depth_stage_frames < cap) {
+    UWT_CUDA(t, cudaStreamSynchronize(t->stream));
+    cudaFree(t->d_depth_stage);
+    t->d_depth_stage = nullptr;
+    t->depth_stage_frames = 0;
+    UWT_CUDA(t, cudaMalloc(&t->d_depth_stage, cap * dense_frame));
+    t->depth_stage_frames = cap;
   }
-  ArgRegion* r = nullptr;
-  if ((rc = acquire(t, &r))) return rc;
-  if ((rc = push_slots(t, r, n, slots, nullptr))) return rc;
-  ProfSpan span(t, UWT_K_PYRAMID);
-  const int k = launch_depth_pyramid(t->geom, t->pools, n, r->d_int, t->stream);
-  span.done(k);
-  if (k < 0) return fail(t, UWT_E_CUDA, "depth pyramid kernel launch failed: %s",
-                         cudaGetErrorString(cudaGetLastError()));
-  t->launches += k;
-  if ((rc = release(t, r))) return rc;
+  for (size_t done = 0; done < (size_t)n; done += cap) {
+    const size_t cnt = std::min(cap, (size_t)n - done);
+    const uint8_t* csrc = src + done * frame_stride;
+    size_t rs = row_stride, fs = frame_stride;
+    if (!on_device) {
+      if (frame_stride == row_stride * h) {
+        UWT_CUDA(t, cudaMemcpy2DAsync(t->d_depth_stage, dense_row, csrc, row_stride, dense_row,
+                                      h * cnt, cudaMemcpyHostToDevice, t->stream));
+      } else {
+        for (size_t i = 0; i < cnt; ++i)
+          UWT_CUDA(t, cudaMemcpy2DAsync(t->d_depth_stage + i * dense_frame, dense_row,
+                                        csrc + i * frame_stride, row_stride, dense_row, h,
+                                        cudaMemcpyHostToDevice, t->stream));
+      }
+      csrc = t->d_depth_stage;
+      rs = dense_row;
+      fs = frame_stride == 0 ? 0 : dense_frame;
+      if (frame_stride == 0 && cnt > 1) fs = 0;  // one host frame for every slot
+    }
+    ArgRegion* r = nullptr;
+    if ((rc = acquire(t, &r))) return rc;
+    if ((rc = push_slots(t, r, (int)cnt, slots + done, nullptr))) return rc;
+    ProfSpan span(t, UWT_K_PYRAMID);
+    int k = launch_depth_import(t->geom, t->pools, (int)cnt, r->d_int, csrc, rs, fs, t->stream);
+    const int k2 = k < 0 ? -1 : launch_depth_pyramid(t->geom, t->pools, (int)cnt, r->d_int, t->stream);
+    k = (k < 0 || k2 < 0) ? -1 : k + k2;
+    span.done(k);
+    if (k < 0) return fail(t, UWT_E_CUDA, "depth pyramid kernel launch failed: %s",
+                           cudaGetErrorString(cudaGetLastError()));
+    t->launches += k;
+    if ((rc = release(t, r))) return rc;
+  }
   for (int i = 0; i < n; ++i) {
     SlotState& s = t->slots[slots[i]];
     s.depth = true;

@@ -529,12 +529,17 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
       // the fast loop assumes the reference's integer residual scale and principal points away
       // from 0 (Geom::exact_div); anything else, levels beyond 4, depth input and bilinear
       // sampling run the generic loop
-      const bool fast = kMode == kFlowMono && fast_sweep_applies(geom, lvl);
+      const bool fast = (kMode == kFlowMono && fast_sweep_applies(geom, lvl)) ||
+                        (kMode == kFlowDepth && fast_depth_sweep_applies(geom, lvl));
       switch (fast ? 1 : 0) {  // CTA-uniform
         case 1:
-          fast_sweep<kWeighted, kTab>(geom, lvl, recs, lo + tid, hi, kFlowThreads, rec0, rec1,
-                                      tabx, taby, tab_x, tab_y, I2, rscale, acc, sum_r2, n_val,
-                                      lut);
+          if constexpr (kMode == kFlowDepth)
+            fast_depth_sweep(geom, lvl, recs, recz, lo + tid, hi, kFlowThreads, tabx, tab_x, I2,
+                             rscale, acc, sum_r2, n_val);
+          else
+            fast_sweep<kWeighted, kTab>(geom, lvl, recs, lo + tid, hi, kFlowThreads, rec0, rec1,
+                                        tabx, taby, tab_x, tab_y, I2, rscale, acc, sum_r2, n_val,
+                                        lut);
           break;
         default: {
           int i = lo + tid;

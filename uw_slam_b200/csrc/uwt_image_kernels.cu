@@ -196,6 +196,39 @@ depth_down_kernel(const __grid_constant__ Geom geom, const Pools pools,
     *o = (uint16_t)o0;
 }
 
+// Level 0 of the depth pyramid for n slots from frames in DEVICE memory (the caller's, or the
+// upload staging buffer): frame i at src + i * frame_stride bytes (0 = every slot gets the same
+// frame), rows row_stride bytes apart.  One launch instead of one 2-D copy per slot.
+__global__ void __launch_bounds__(256)
+depth_import_kernel(const __grid_constant__ Geom geom, const Pools pools,
+                    const int* __restrict__ slots, const uint8_t* __restrict__ src,
+                    size_t row_stride, size_t frame_stride, int vec) {
+  const LevelGeom& L = geom.lv[0];
+  const int slot = slots[blockIdx.z];
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 8;
+  if (x >= L.w || y >= L.h) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * frame_stride + (size_t)y * row_stride + 2 * (size_t)x;
+  uint16_t* d = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off + (size_t)y * L.pitch + x;
+  if (vec) {  // the width is a multiple of 16 pixels: a group of 8 is all in or all out
+    *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(s));
+  } else {
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = s16[i];
+  }
+}
+
+int launch_depth_import(const Geom& g, const Pools& p, int n, const int* d_slots,
+                        const uint8_t* d_src, size_t row_stride, size_t frame_stride,
+                        cudaStream_t st) {
+  const LevelGeom& L = g.lv[0];
+  const int vec = ((((uintptr_t)d_src) | row_stride | frame_stride) & 15) == 0 ? 1 : 0;
+  dim3 grid((L.w + 511) / 512, (L.h + 3) / 4, n);
+  depth_import_kernel<<<grid, 256, 0, st>>>(g, p, d_slots, d_src, row_stride, frame_stride, vec);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_depth_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots,
                          cudaStream_t st) {
   int k = 0;

@@ -205,6 +205,9 @@ bool frame_fused_supported(const Geom& g);
 int launch_frame_fused(const Geom& g, const Pools& p, int n, const int* d_slots,
                        const uint8_t* src, size_t row_stride, size_t frame_stride,
                        cudaStream_t st);
+int launch_depth_import(const Geom& g, const Pools& p, int n, const int* d_slots,
+                        const uint8_t* d_src, size_t row_stride, size_t frame_stride,
+                        cudaStream_t st);
 int launch_depth_pyramid(const Geom& g, const Pools& p, int n, const int* d_slots,
                          cudaStream_t st);
 int launch_remap(const uint8_t* d_src, size_t row_stride, int in_w, int in_h, const short2* map1,
