@@ -8,7 +8,7 @@ mkdir -p build/variants
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-    -fmad=false -Xcompiler -fPIC -shared -cudart static $flags \
+    -fmad=false -Xcompiler -fPIC -Xcompiler -ffp-contract=off -shared -cudart static $flags \
     -o build/variants/$name.so uw_slam_b200/csrc/*.cu &
 done
 wait

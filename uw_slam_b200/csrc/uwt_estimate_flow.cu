@@ -225,34 +225,6 @@ __device__ bool flow_advance(const Geom& geom, const Pools& pools, const Estimat
   return flow_enter_level(geom, pools, io, prob, fp, zero_tot, lane, nprob);
 }
 
-// Warms the L2 for the sweep that is about to be published: the level's packed records of the
-// previous frame and the level's image of the current frame, as bulk L2 prefetches (one
-// instruction per 32 KB piece, issued by the lanes of the publishing warp).  With 128 problems in
-// flight the working set (170 MB at level 1 of 1280x1024) exceeds the L2, so a sweep's first
-// touches would otherwise pay DRAM latency inside the point loop.
-__device__ __forceinline__ void l2_prefetch_range(const void* base, size_t bytes, int lane) {
-  const uintptr_t a0 = ((uintptr_t)base + 15) & ~(uintptr_t)15;
-  const uintptr_t a1 = ((uintptr_t)base + bytes) & ~(uintptr_t)15;
-  constexpr uintptr_t kPiece = 32768;
-  for (uintptr_t a = a0 + (uintptr_t)lane * kPiece; a < a1; a += 32 * kPiece) {
-    const uint32_t sz = (uint32_t)(a1 - a < kPiece ? a1 - a : kPiece);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(sz) : "memory");
-  }
-}
-__device__ __forceinline__ void flow_prefetch_level(const Geom& geom, const Pools& pools,
-                                                    const EstimateIO& io, int prob,
-                                                    const FlowProblem& fp, int lane) {
-#ifdef UWT_NO_L2_PREFETCH  // A/B knob
-  return;
-#endif
-  const LevelGeom& L = geom.lv[fp.lvl];
-  const int prev_slot = io.prev_slots[prob], cur_slot = io.cur_slots[prob];
-  l2_prefetch_range(pools.rec + (size_t)prev_slot * geom.rec_elems + L.rec_off,
-                    (size_t)fp.n * sizeof(uint64_t), lane);
-  l2_prefetch_range(pools.img + (size_t)cur_slot * geom.plane_elems + L.plane_off,
-                    (size_t)L.pitch * L.h, lane);
-}
-
 // Publishes the new state of a problem: either its final pose, or its next sweep's tasks.
 __device__ __forceinline__ void flow_commit(const EstimateIO& io, int prob, const FlowProblem& fp,
                                             bool finished, FlowCtl* ctl, unsigned long long* ring,
@@ -364,7 +336,6 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
       fp.lvl = geom.first_level;
       fp.phase = tukey ? 1 : 0;
       const bool finished = flow_enter_level(geom, pools, io, prob, fp, sh.tot, lane, nprob);
-      if (!finished) flow_prefetch_level(geom, pools, io, prob, fp, lane);
       flow_commit(io, prob, fp, finished, ctl, ring, cap, probs, lane);
     }
   }
@@ -413,7 +384,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     const uint64_t rec1 = (left0 > kFlowThreads) ? __ldg(&recs[lo + tid + kFlowThreads]) : rec0;
     // tables over ALL columns of the level: no dependent read of the chunk's first / last record
     // (x-major order would allow a narrower table) on the critical path of the hand-over
-    constexpr int xlo = 0;
+    constexpr int xlo = 0;  // tables start at column 0
     if constexpr (kMode == kFlowDepth) {
       // per-sweep rigid transform as 12 doubles T[r][0..3] (Tracker.cpp:1423-1425)
       if (tid < 12) {
@@ -615,8 +586,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
         if (tr) fp.ntrace += 1;
         __syncwarp();
         const bool finished = flow_advance(geom, pools, io, prob, fp, brk, sh.tot, lane, nprob);
-        if (!finished) flow_prefetch_level(geom, pools, io, prob, fp, lane);
-        flow_commit(io, prob, fp, finished, ctl, ring, cap, probs, lane);
+          flow_commit(io, prob, fp, finished, ctl, ring, cap, probs, lane);
       }
     }
     __syncthreads();  // next task published; tables and warp_part are free for reuse
