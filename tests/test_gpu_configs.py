@@ -186,3 +186,72 @@ def test_randomised_small_configurations(oracle):
                                   last_level=last, **okw)
         assert np.array_equal(pose, oracle.estimate_pose(p, rp, rc)[0]), tag
         t.close()
+
+
+@pytest.mark.parametrize("batch", [1, 32])
+def test_principal_point_at_zero_uses_exact_division(oracle, batch):
+    """cx = 0.5 puts the level-1 principal point at exactly 0 (Tracker.cpp:321: (cx + 0.5) / 2 -
+    0.5): the shared-reciprocal shortcut of the fast sweep is not provably exact there
+    (docs/ARITHMETIC.md, implementation notes), so the handle takes the generic IEEE division for
+    every point (Geom::exact_div).  Same parity bar: every sweep against the oracle."""
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    w, h = 160, 128
+    fx, fy, cx, cy = 0.8 * w, 0.82 * w, 0.5, h / 2 - 0.5
+    synth.CALIB["_cfg0"] = (w, h, fx, fy, cx, cy)
+    pairs = [synth.render_pair("_cfg0", 70 + i)[:2] for i in range(batch)]
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=2 * batch, flags=L.FLAG_TRACE)
+    assert t.level_info(1).cx == 0.0
+    fp = t.AddFrames(list(range(batch)), np.stack([p[0] for p in pairs]))
+    fc = t.AddFrames(list(range(batch, 2 * batch)), np.stack([p[1] for p in pairs]))
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    poses = t.EstimatePose(fp, fc)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for i in range(batch):
+        rp = oracle.FrameData(pairs[i][0])
+        rc = oracle.FrameData(pairs[i][1], with_candidates=False)
+        opose, _, otr = oracle.estimate_pose(p, rp, rc)
+        tr = t.get_trace(i)
+        assert [(a.level, a.k, a.n_valid, a.sum_r2) for a in tr] == \
+            [(b.level, b.k, b.n_valid, b.sum_r2) for b in otr], i
+        for a, b in zip(tr, otr):
+            assert np.array_equal(np.array(a.A[:]), np.array(b.A[:])), (i, b.level, b.k)
+        assert np.array_equal(poses[i], opose), i
+    t.close()
+
+
+@pytest.mark.parametrize("batch", [1, 32])
+def test_points_outside_the_division_window(oracle, batch):
+    """Initial poses that put Z' at 0 or at ~2^-64 (outside the [2^-60, 2^60) window of the
+    shared-reciprocal division): the fast sweep defers those points to the generic IEEE path.
+    Every quantity must still equal the oracle's (here: all points invalid, rule U2)."""
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    calib = "small"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    prev, cur, _, _ = synth.render_pair(calib, 9)
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=max(2, batch), flags=L.FLAG_TRACE)   # n <= max_frames
+    t.AddFrames([0, 1], np.stack([prev, cur]))
+    t.ApplyGradient([0])
+    t.ObtainCandidatePoints([0])
+    a = np.float32(1e-19)
+    inits = [np.array([0, 0, 0, 1, 0, 0, -1], np.float32),                    # Z' == 0
+             np.array([a / 2, 0, 0, 1, 0, 0, -1], np.float32),                # |Z'| ~ 2^-64
+             np.array([0, 0, 0, 1, 0.01, 0, 0], np.float32)]                  # a normal one
+    init = np.stack([inits[i % 3] for i in range(batch)])
+    poses, stats = t.EstimatePose([0] * batch, [1] * batch, init_poses=init, return_stats=True)
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    rp, rc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
+    for i in range(batch):
+        opose, ost, otr = oracle.estimate_pose(p, rp, rc, init_pose=init[i])
+        assert np.array_equal(poses[i], opose, equal_nan=True), (i, poses[i], opose)
+        assert list(stats[i].evaluations)[:5] == list(ost.evaluations)[:5], i
+        tr = t.get_trace(i)
+        assert [(x.level, x.k, x.n_valid, x.sum_r2) for x in tr] == \
+            [(y.level, y.k, y.n_valid, y.sum_r2) for y in otr], i
+    t.close()
