@@ -7,7 +7,7 @@ namespace uwt {
 // ----------------------------------------------------------------------------------------
 // Batched Gauss-Newton as a persistent DATAFLOW kernel (many independent problems).
 //
-// The cluster kernel above gives every problem a fixed set of CTAs for its whole life: CTAs idle
+// The cluster kernel (uwt_estimate.cu) gives every problem a fixed set of CTAs for its whole life: CTAs idle
 // at every per-sweep barrier, during the serial solve, and when problems of a wave finish at
 // different times (measured: 20 % of the launch is tail, 14 % barrier stalls).  Here the unit of
 // scheduling is one CHUNK of one residual sweep (kFlowChunk consecutive candidate records of one
@@ -17,8 +17,11 @@ namespace uwt {
 // for that problem and enqueues the chunks of its next sweep.  No grid- or cluster-wide barrier
 // exists: a problem's update overlaps every other problem's streaming, chunks are equal-sized,
 // and the GPU drains only when the last problems run out of sweeps.
-//   * x-major record order => a chunk spans few image columns: the per-task transform tables are
-//     tab_y[3][h] plus tab_x[3][columns of the chunk] (cheap to rebuild per task)
+//   * the per-task transform tables tab_x[3][kTab], tab_y[3][kTab] (compile-time row stride, all
+//     columns and rows of the level) are rebuilt per task from the problem's pose: no dependent
+//     read of the chunk's records sits on the hand-over path
+//   * the point loop is the software-pipelined fast sweep of uwt_estimate_common.cuh (mono input,
+//     nearest sampling; depth has its own pipelined sweep, everything else the generic loop)
 //   * waits are bounded by construction: a consumer spins only on a ring slot whose producer is
 //     a CTA that holds a real task, and leaves when the count of unfinished problems is zero
 //   * arithmetic, and therefore every result, is identical to the cluster kernel's
@@ -384,7 +387,6 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     const uint64_t rec1 = (left0 > kFlowThreads) ? __ldg(&recs[lo + tid + kFlowThreads]) : rec0;
     // tables over ALL columns of the level: no dependent read of the chunk's first / last record
     // (x-major order would allow a narrower table) on the critical path of the hand-over
-    constexpr int xlo = 0;  // tables start at column 0
     if constexpr (kMode == kFlowDepth) {
       // per-sweep rigid transform as 12 doubles T[r][0..3] (Tracker.cpp:1423-1425)
       if (tid < 12) {
@@ -408,7 +410,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
             PointGeom pg;
             int i1;
             const uint8_t* target;
-            if (point_geometry<false>(wc, __ldg(&recs[i]), tab_x - xlo, table_w, tab_y, table_h,
+            if (point_geometry<false>(wc, __ldg(&recs[i]), tab_x, table_w, tab_y, table_h,
                                       I2, pg, i1, target))
               atomicAdd(&fr.hist[(int)__ldg(target) - i1 + 255], 1u);
           }
@@ -495,7 +497,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     for (int i = 0; i < kNQ; ++i) acc[i] = 0.0;
     unsigned sum_r2 = 0, n_val = 0;
     {
-      const uint32_t tabx = (uint32_t)__cvta_generic_to_shared(tab_x) - (uint32_t)xlo * 8u;
+      const uint32_t tabx = (uint32_t)__cvta_generic_to_shared(tab_x);
       const uint32_t taby = (uint32_t)__cvta_generic_to_shared(tab_y);
       // the fast loop assumes the reference's integer residual scale and principal points away
       // from 0 (Geom::exact_div); anything else, levels beyond 4, depth input and bilinear
@@ -523,7 +525,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
                                         n_val);
             else
               accumulate_point<kWeighted, kMode == kFlowDepth>(
-                  wc, rec, tab_x - xlo, table_w, tab_y, table_h, I2, rscale, rscale_is_int,
+                  wc, rec, tab_x, table_w, tab_y, table_h, I2, rscale, rscale_is_int,
                   rscale_i, acc, sum_r2, n_val, lut,
                   kMode == kFlowDepth ? (int)__ldg(&recz[i]) : 0);
             rec = rec_next;
