@@ -201,6 +201,7 @@ struct ProfSpan {
 int build_geom(const uwt_config& c, Geom& g) {
   std::memset(&g, 0, sizeof(g));
   g.levels = c.levels;
+  g.max_slots = c.max_frames;
   g.first_level = c.first_level;
   g.last_level = c.last_level;
   g.max_iterations = c.max_iterations;

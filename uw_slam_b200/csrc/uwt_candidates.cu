@@ -18,6 +18,8 @@
 //             the packed 8-byte record (x, y, I1, gx, gy) the Gauss-Newton kernel streams;
 //             I1 and the Scharr gx, gy of a selected pixel come from an image tile with a
 //             one-pixel halo in shared memory (no int16 gradient planes are read).
+#include <string.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -95,31 +97,14 @@ __device__ __forceinline__ void load_img_tile_halo(const uint8_t* __restrict__ p
   }
 }
 
-// Scharr x / y at image pixel (x, y) from the halo tile (Tracker.cpp:1133-1134): the same
-// integers as K2's gradient_kernel.  BORDER_REFLECT_101 is already written into the halo
-// (patch_img_tile_borders), so a pixel is three unaligned 4-byte windows and five dp4a.
+// Scharr x / y from the halo tile (Tracker.cpp:1133-1134): the same integers as the frame
+// kernel's.  BORDER_REFLECT_101 is already written into the halo (patch_img_tile_borders), so a
+// pixel is three 4-byte windows and five dp4a.
 __device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t wgt, int acc) {
   int d;
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
   return d;
 }
-__device__ __forceinline__ uint32_t window_at(const uint8_t* tile, int off) {
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(tile + (off & ~3));
-  return __funnelshift_r(p[0], p[1], 8 * (off & 3));
-}
-__device__ __forceinline__ void scharr_from_tile(const uint8_t* tile, int x0, int y0, int x, int y,
-                                                 const StencilWeights& sw, int& gx, int& gy,
-                                                 int& center) {
-  // byte offset of pixel (x - 1, y - 1) inside the tile
-  const int off = (y - y0) * kImgTilePitch + (x - x0 + 3);
-  const uint32_t top = window_at(tile, off);
-  const uint32_t mid = window_at(tile, off + kImgTilePitch);
-  const uint32_t bot = window_at(tile, off + 2 * kImgTilePitch);
-  center = (mid >> 8) & 0xFF;
-  gx = dp4a_us(top, sw.d, dp4a_us(mid, sw.dm, dp4a_us(bot, sw.d, 0)));
-  gy = dp4a_us(bot, sw.sp, dp4a_us(top, sw.sm, 0));
-}
-
 // Writes the reflected border pixels (x = -1 -> 1, x = w -> w-2, then y = -1 -> 1, y = h -> h-2)
 // into the halo of an image tile.  Block-wide; only tiles on the image border do any work.
 __device__ __forceinline__ void patch_img_tile_borders(uint8_t* tile, const LevelGeom& L, int x0,
@@ -267,85 +252,241 @@ cand_scan_kernel(const __grid_constant__ Geom geom, const Pools pools,
   if (t == 1023) pools.ncand[(size_t)slot * kMaxLevels + lvl] = warp_tot[31];
 }
 
+// ---- scatter ----------------------------------------------------------------------------
+// Tiles arrive by 2-D tensor copies (cp.async.bulk.tensor on per-level maps of the gradient and
+// image pools, SASS UTMALDG; parts outside the image read as zero) into double-buffered shared
+// memory: the copy of the next tile runs while this one is processed, and no thread spends
+// instructions on addresses.
+constexpr int kScImgW = kStripW + 32;           // image box: columns [x0 - 16, x0 + 144): the first
+                                                // coordinate of a tensor copy is 16-byte aligned
+constexpr int kScImgH = kSegRows + 2;           //            rows    [y0 - 1, y0 + 65)
+constexpr int kScDerivPitch = kStripW + 4;      // words per row of the derivative tile (16-byte rows)
+constexpr uint32_t kScTileBytes = kStripW * kSegRows + kScImgW * kScImgH;
+struct ScatterShared {
+  alignas(128) uint8_t sg[2][kStripW * kSegRows];      // gradient-image tile, pitch 128
+  alignas(128) uint8_t si[2][kScImgW * kScImgH + 64];  // image tile + halo, pitch 160 (size % 128 = 0)
+  alignas(16) uint32_t sd[kSegRows * kScDerivPitch];   // gx:13 | gy:13 << 13 of every pixel
+  alignas(16) uint32_t cm[(kSegRows / 8) * (kStripW / 4)];  // [band][column group]: byte i = 8-row
+                                                            // selection mask of column 4*group + i
+  alignas(8) uint64_t bar[2];
+};
+struct ScatterMaps {
+  CUtensorMap g[kMaxLevels];
+  CUtensorMap img[kMaxLevels];
+};
+
+__device__ __forceinline__ uint32_t sc_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void sc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(sc_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void sc_tma_load_3d(void* dst, const CUtensorMap* map, int x, int y,
+                                               int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(sc_smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(sc_smem_u32(bar))
+      : "memory");
+}
+
+// BORDER_REFLECT_101 into the halo of the image tile (x = -1 -> 1, x = w -> w - 2, then
+// y = -1 -> 1, y = h -> h - 2 including the patched columns).  Only border tiles do any work.
+__device__ __forceinline__ void sc_patch_borders(uint8_t* tile, const LevelGeom& L, int x0, int y0,
+                                                 int t) {
+  const bool edge_l = (x0 == 0), edge_r = (x0 + kStripW >= L.w);
+  const bool edge_t = (y0 == 0), edge_b = (y0 + kSegRows >= L.h);
+  if (edge_l || edge_r) {
+    if (t < kScImgH) {
+      uint8_t* row = tile + t * kScImgW;
+      if (edge_l) row[15] = row[17];
+      if (edge_r) {
+        const int cx = L.w - x0 + 16;
+        row[cx] = row[cx - 2];
+      }
+    }
+    __syncthreads();
+  }
+  if (edge_t || edge_b) {
+    constexpr int kRowWords = kScImgW / 4;
+    if (t < kRowWords) {
+      uint32_t* rows = reinterpret_cast<uint32_t*>(tile);
+      if (edge_t) rows[t] = rows[2 * kRowWords + t];
+      if (edge_b) {
+        const int ry = L.h - (y0 - 1);  // tile row of image row h
+        rows[ry * kRowWords + t] = rows[(ry - 2) * kRowWords + t];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Two phases per 128 x 64 tile, both free of shared-memory bank conflicts:
+//   dense  : warp = 8-row band, lane = 4-pixel column group.  A thread slides a 3-row window
+//            down its band (three shared loads per 4 pixels), evaluates Scharr x / y
+//            (Tracker.cpp:1133-1134; the frame kernel's integers) for every pixel, stores
+//            gx | gy << 13 -- the upper word of the packed record -- with one 16-byte store per
+//            row, and thresholds the gradient image four pixels at a time: `acc |= sel4 << row`
+//            leaves the 8-row selection mask of each of its 4 columns in one byte of a register;
+//   column : a warp walks 4 columns x 8 rows per step (lane = (row, column): the derivative
+//            tile's 132-word pitch spreads these over all 32 banks).  Every lane keeps the
+//            running output offset of its column (x outer, y inner: Tracker.cpp:1334-1335), so
+//            a selected pixel's slot is base + popc(mask below its row): no ballots, and a
+//            record is two shared loads, three logic operations and one 8-byte store.
+// The first form of this kernel evaluated the stencil inside the divergent branch of a
+// column walk and copied its tiles with 4-byte cp.async: 19.7 k warp instructions per tile.
 template <bool kDepth>
 __global__ void __launch_bounds__(256)
 cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
                     const int* __restrict__ slots, int n_slots, int item_begin, int item_count,
-                    const StencilWeights sw) {
-  __shared__ __align__(16) uint8_t sg[2][kSegRows * kTilePitch8];
-  __shared__ __align__(16) uint8_t si[2][kImgTileRows * kImgTilePitch];
+                    const StencilWeights sw, const __grid_constant__ ScatterMaps maps) {
+  extern __shared__ __align__(128) uint8_t scatter_smem[];
+  ScatterShared& sh = *reinterpret_cast<ScatterShared*>(scatter_smem);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int total = item_count * n_slots;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  auto issue = [&](int work, int buf) {
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sc_smem_u32(&sh.bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sc_smem_u32(&sh.bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int work, int buf) {  // thread 0 only
     const TileItem it = locate_item(geom, work % item_count + item_begin);
     const int slot = slots[work / item_count];
-    const LevelGeom& L = geom.lv[it.lvl];
-    const size_t pbase = (size_t)slot * geom.plane_elems + L.plane_off;
-    load_tile_u8(pools.g + pbase, L, it.strip * kStripW, it.seg * kSegRows, sg[buf], t);
-    if (L.rec_off >= 0)
-      load_img_tile_halo(pools.img + pbase, L, it.strip * kStripW, it.seg * kSegRows, si[buf], t);
-    cp_async_commit();
+    const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
+    // the buffers were read (and the image tile patched) through the generic proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                     sc_smem_u32(&sh.bar[buf])),
+                 "r"(kScTileBytes)
+                 : "memory");
+    sc_tma_load_3d(sh.sg[buf], &maps.g[it.lvl], x0, y0, slot, &sh.bar[buf]);
+    sc_tma_load_3d(sh.si[buf], &maps.img[it.lvl], x0 - 16, y0 - 1, slot, &sh.bar[buf]);
   };
   int work = blockIdx.x, buf = 0;
-  if (work < total) issue(work, 0);
+  uint32_t phases = 0u;  // bit b: parity the next wait on bar[b] expects
+  if (work < total && t == 0) issue(work, 0);
   for (; work < total; work += gridDim.x, buf ^= 1) {
     const int next = work + gridDim.x;
-    if (next < total) {
-      issue(next, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    if (next < total && t == 0) issue(next, buf ^ 1);
+    sc_mbar_wait(&sh.bar[buf], (phases >> buf) & 1u);
+    phases ^= 1u << buf;
     const TileItem it = locate_item(geom, work % item_count + item_begin);
     const int slot = slots[work / item_count];
     const LevelGeom& L = geom.lv[it.lvl];
     const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
     const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
-    const bool has_rec = L.rec_off >= 0;
-    const uint8_t* tg = sg[buf];
-    const uint8_t* ti = si[buf];
-    if (has_rec) patch_img_tile_borders(si[buf], L, x0, y0, t);
+    const uint8_t* tg = sh.sg[buf];
+    uint8_t* ti = sh.si[buf];
     const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
-    uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0);
-    constexpr bool use_depth = kDepth;
+    uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + L.rec_off;
     const bool all_points = kDepth && geom.depth_mode == UWT_DEPTH_ALL_POINTS;
     const uint16_t* dplane = kDepth ? pools.dep + (size_t)slot * geom.plane_elems + L.plane_off
                                     : nullptr;
-    uint16_t* recz =
-        kDepth ? pools.recz + (size_t)slot * geom.rec_elems + (has_rec ? L.rec_off : 0) : nullptr;
-    // start offsets of this warp's 16 (column, segment) runs: one per lane
-    uint32_t my_base = 0;
+    uint16_t* recz = kDepth ? pools.recz + (size_t)slot * geom.rec_elems + L.rec_off : nullptr;
+    sc_patch_borders(ti, L, x0, y0, t);
+    // ---- dense phase ----
     {
-      const int x = x0 + wid * 16 + lane;
-      if (lane < 16 && x < L.w) my_base = cnt[(size_t)x * L.nseg + it.seg];
-    }
-#pragma unroll 2
-    for (int j = 0; j < 16; ++j) {
-      const int c = wid * 16 + j, x = x0 + c;
-      uint32_t base = __shfl_sync(0xffffffffu, my_base, j);
-      if (x >= L.w) break;  // warp-uniform
+      const int band = wid, xg = x0 + 4 * lane;
+      uint32_t acc = 0;
+      if (xg < L.w && y0 + band * 8 < L.h) {
+        // image-tile row of image row y0 + band * 8 - 1; words: [3 + lane] left of the group,
+        // [4 + lane] the group, [5 + lane] right of it
+        const uint32_t* ir = reinterpret_cast<const uint32_t*>(ti + (band * 8) * kScImgW) + lane + 3;
+        const uint32_t* gr = reinterpret_cast<const uint32_t*>(tg + (band * 8) * kStripW) + lane;
+        uint4* out = reinterpret_cast<uint4*>(sh.sd + (band * 8) * kScDerivPitch + 4 * lane);
+        constexpr int kIW = kScImgW / 4;
+        uint32_t tw[4], mw[4];
+        {
+          const uint32_t l = ir[0], c = ir[1], r = ir[2];
+          tw[0] = __funnelshift_r(l, c, 24), tw[1] = c, tw[2] = __funnelshift_r(c, r, 8),
+          tw[3] = __funnelshift_r(c, r, 16);
+          const uint32_t l1 = ir[kIW], c1 = ir[kIW + 1], r1 = ir[kIW + 2];
+          mw[0] = __funnelshift_r(l1, c1, 24), mw[1] = c1, mw[2] = __funnelshift_r(c1, r1, 8),
+          mw[3] = __funnelshift_r(c1, r1, 16);
+        }
+        const uint32_t thr4 = min(ithr, 255u) * 0x01010101u;
+        // bytes of the group beyond the image width never count (all-points mode has no
+        // gradient test; elsewhere their gradient is zero anyway)
+        const int nvalid = min(4, L.w - xg);
+        const uint32_t vmask = nvalid == 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - nvalid)));
 #pragma unroll
-      for (int ch = 0; ch < kSegRows / 32; ++ch) {
-        const int row = ch * 32 + lane, y = y0 + row;
-        bool sel = (y < L.h) && (all_points || (uint32_t)tg[row * kTilePitch8 + c] > ithr);
-        int dz = 0;
-        if (use_depth && sel) {  // Tracker.cpp:1339: depth != 0 as well
-          dz = depth_at(dplane, L.pitch, x, y, geom.depth_mode);
-          sel = dz != 0;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t l = ir[(j + 2) * kIW], c = ir[(j + 2) * kIW + 1], r = ir[(j + 2) * kIW + 2];
+          const uint32_t bw[4] = {__funnelshift_r(l, c, 24), c, __funnelshift_r(c, r, 8),
+                                  __funnelshift_r(c, r, 16)};
+          uint32_t d[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int gx = dp4a_us(tw[i], sw.d, dp4a_us(mw[i], sw.dm, dp4a_us(bw[i], sw.d, 0)));
+            const int gy = dp4a_us(bw[i], sw.sp, dp4a_us(tw[i], sw.sm, 0));
+            d[i] = ((uint32_t)gx & 0x1FFFu) | (((uint32_t)gy & 0x1FFFu) << 13);
+            tw[i] = mw[i];
+            mw[i] = bw[i];
+          }
+          out[j * (kScDerivPitch / 4)] = make_uint4(d[0], d[1], d[2], d[3]);
+          uint32_t sel4 = all_points ? 0x01010101u : __vsetgtu4(gr[j * (kStripW / 4)], thr4);
+          if (y0 + band * 8 + j >= L.h) sel4 = 0u;
+          acc |= (sel4 & vmask) << j;
         }
-        const uint32_t b = __ballot_sync(0xffffffffu, sel);
-        if (sel) {
-          const uint32_t o = base + __popc(b & lt_mask);
-          if (has_rec && use_depth) recz[o] = (uint16_t)dz;
-          // a record carries (x, y) itself; levels without records never reach this kernel
-          // (cand_mask_kernel keeps their selection as a bitmask)
-          int gx, gy, i1;
-          scharr_from_tile(ti, x0, y0, x, y, sw, gx, gy, i1);
-          rec[o] = pack_record((uint32_t)x, (uint32_t)y, (uint32_t)i1, gx, gy);
+      }
+      sh.cm[band * (kStripW / 4) + lane] = acc;
+    }
+    __syncthreads();
+    // ---- column phase: 4 columns x 8 rows per step ----
+    {
+      const int cq = lane & 3, rq = lane >> 2;
+      const uint32_t below = (1u << rq) - 1u;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int cg = wid * 4 + q;           // column group of this step
+        const int c = cg * 4 + cq, x = x0 + c;
+        if (x0 + cg * 4 >= L.w) break;        // warp-uniform
+        uint32_t base = (x < L.w) ? __ldg(&cnt[(size_t)x * L.nseg + it.seg]) : 0u;
+        const uint8_t* cmb = reinterpret_cast<const uint8_t*>(sh.cm) + cg * 4 + cq;
+        const uint32_t* dcol = sh.sd + rq * kScDerivPitch + c;
+        const uint8_t* icol = ti + (rq + 1) * kScImgW + 16 + c;
+        uint32_t xy = (uint32_t)x | ((uint32_t)(y0 + rq) << 12);
+#pragma unroll
+        for (int b = 0; b < kSegRows / 8; ++b) {
+          const uint32_t m8 = cmb[b * kStripW];
+          bool sel = (m8 >> rq) & 1u;
+          uint32_t o = base + __popc(m8 & below);
+          if constexpr (kDepth) {
+            // Tracker.cpp:1339: depth != 0 as well.  The count kernel applied the same test, so
+            // the offsets come from a ballot over the pixels that pass both.
+            int dz = 0;
+            if (sel) {
+              dz = depth_at(dplane, L.pitch, x, y0 + b * 8 + rq, geom.depth_mode);
+              sel = dz != 0;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, sel);
+            // lanes of column cq sit at bit positions cq, cq + 4, ...: rows below this lane's
+            const uint32_t colbits = bal & (0x11111111u << cq);
+            o = base + __popc(colbits & ((1u << lane) - 1u));
+            if (sel) recz[o] = (uint16_t)dz;
+            base += __popc(colbits);
+          } else {
+            base += __popc(m8);
+          }
+          if (sel) {
+            const uint32_t i1 = icol[b * 8 * kScImgW];
+            const uint32_t hi = dcol[b * 8 * kScDerivPitch];
+            rec[o] = (uint64_t)(xy | (i1 << 24)) | ((uint64_t)hi << 32);
+          }
+          xy += 8u << 12;
         }
-        base += __popc(b);
       }
     }
     __syncthreads();  // both buffers of this stage are refilled in the next iteration
@@ -435,21 +576,38 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   // persistent grids: a multiple of the 148 SMs, as many CTAs per SM as the double-buffered
   // tiles allow; small jobs get one CTA per work item
   const long long total = (long long)lr.item_count * n;
-  // same for every device of a box; computed once, published together (handles may be driven
-  // from different host threads)
+  // occupancy is the same for every device of a box: computed once, published together (handles
+  // may be driven from different host threads); the dynamic shared-memory limit of the scatter
+  // kernel is a per-device function attribute and is raised once per device
   static int per_sm_count = 0, per_sm_scatter = 0, sms = 0;
-  static std::once_flag occupancy_once;
-  std::call_once(occupancy_once, [] {
+  static std::mutex attr_mutex;
+  static bool attr_set[64] = {};
+  {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, cand_count_kernel<false>, 256, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, cand_scatter_kernel<false>, 256,
-                                                  0);
-    if (sms <= 0) sms = 148;
-    if (per_sm_count <= 0) per_sm_count = 4;
-    if (per_sm_scatter <= 0) per_sm_scatter = 4;
-  });
+    std::lock_guard<std::mutex> lock(attr_mutex);
+    bool& set = attr_set[(dev < 0 ? 0 : dev) % 64];
+    if (!set) {
+      if (cudaFuncSetAttribute(cand_scatter_kernel<false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(ScatterShared)) != cudaSuccess ||
+          cudaFuncSetAttribute(cand_scatter_kernel<true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(ScatterShared)) != cudaSuccess)
+        return -1;
+      set = true;
+    }
+    if (sms == 0) {
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, cand_count_kernel<false>, 256,
+                                                    0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, cand_scatter_kernel<false>,
+                                                    256, sizeof(ScatterShared));
+      if (per_sm_count <= 0) per_sm_count = 4;
+      if (per_sm_scatter <= 0) per_sm_scatter = 3;
+      if (sms <= 0) sms = 148;
+    }
+  }
   const int grid_count = (int)std::min<long long>(total, (long long)sms * per_sm_count);
   const int grid_scatter = (int)std::min<long long>(total, (long long)sms * per_sm_scatter);
   const bool depth = g.depth_mode != UWT_DEPTH_NONE;
@@ -467,12 +625,22 @@ int launch_candidates(const Geom& g, const Pools& p, int n, const int* d_slots, 
   cand_scan_kernel<<<dim3(sr.lvl_count, n), 1024, 0, st>>>(g, p, d_slots, sr.lvl_begin);
   if (cudaGetLastError() != cudaSuccess) return -1;
   ++launches;
+  ScatterMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int l = lr.lvl_begin; l < lr.lvl_begin + lr.lvl_count; ++l) {
+    const LevelGeom& L = g.lv[l];
+    if (!encode_u8_map3d(&maps.g[l], p.g + L.plane_off, L.pitch, L.h, g.max_slots, L.pitch,
+                         g.plane_elems, kStripW, kSegRows) ||
+        !encode_u8_map3d(&maps.img[l], p.img + L.plane_off, L.pitch, L.h, g.max_slots, L.pitch,
+                         g.plane_elems, kScImgW, kScImgH))
+      return -1;
+  }
   if (depth)
-    cand_scatter_kernel<true><<<grid_scatter, 256, 0, st>>>(
-        g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op));
+    cand_scatter_kernel<true><<<grid_scatter, 256, sizeof(ScatterShared), st>>>(
+        g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op), maps);
   else
-    cand_scatter_kernel<false><<<grid_scatter, 256, 0, st>>>(
-        g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op));
+    cand_scatter_kernel<false><<<grid_scatter, 256, sizeof(ScatterShared), st>>>(
+        g, p, d_slots, n, lr.item_begin, lr.item_count, stencil_weights(g.gradient_op), maps);
   if (cudaGetLastError() != cudaSuccess) return -1;
   ++launches;
   if (with_mask_levels) {

@@ -394,6 +394,21 @@ EncodeTiledFn encode_tiled() {
 
 }  // namespace
 
+// (x, y, frame) map of u8 planes with a box_w x box_h x 1 box, out-of-range parts read as zero.
+bool encode_u8_map3d(CUtensorMap* out, const uint8_t* base, uint64_t w, uint64_t h, uint64_t n,
+                     uint64_t row_stride, uint64_t frame_stride, uint32_t box_w, uint32_t box_h) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  if ((((uintptr_t)base) | row_stride | frame_stride) & 15) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides,
+             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool frame_fused_supported(const Geom& g) { return g.levels <= kFusedMaxLevels; }
 
 // Returns the number of kernels launched (1), -1 on a launch error, or -2 when this source cannot
@@ -403,20 +418,10 @@ int launch_frame_fused(const Geom& g, const Pools& p, int n, const int* d_slots,
                        const uint8_t* src, size_t row_stride, size_t frame_stride,
                        cudaStream_t st) {
   if (!frame_fused_supported(g) || !p.gsum) return -2;
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return -2;
   const LevelGeom& L0 = g.lv[0];
   if (n == 1 || frame_stride == 0) frame_stride = row_stride * (size_t)L0.h;
-  if ((((uintptr_t)src) | row_stride | frame_stride) & 15) return -2;
   CUtensorMap map;
-  const cuuint64_t dims[3] = {(cuuint64_t)L0.w, (cuuint64_t)L0.h, (cuuint64_t)n};
-  const cuuint64_t strides[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
-  const cuuint32_t box[3] = {(cuuint32_t)kF0, (cuuint32_t)kF0, 1u};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(src), dims, strides, box,
-          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return -2;
+  if (!encode_u8_map3d(&map, src, L0.w, L0.h, n, row_stride, frame_stride, kF0, kF0)) return -2;
   const bool sobel = g.gradient_op == UWT_GRADIENT_SOBEL;
   dim3 grid((L0.w + kFT - 1) / kFT, (L0.h + kFT - 1) / kFT, n);
   if (sobel)

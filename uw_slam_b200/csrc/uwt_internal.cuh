@@ -1,5 +1,6 @@
 // uwt_internal.cuh -- shared declarations of libuwtrack (sm_100a only).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +53,7 @@ struct LevelGeom {
 struct Geom {
   LevelGeom lv[kMaxLevels];
   int levels, first_level, last_level, max_iterations;
+  int max_slots;      // slots per pool (uwt_config.max_frames)
   float epsilon, residual_scale;
   double gradient_threshold;
   int solve_mode;
@@ -205,6 +207,10 @@ bool frame_fused_supported(const Geom& g);
 int launch_frame_fused(const Geom& g, const Pools& p, int n, const int* d_slots,
                        const uint8_t* src, size_t row_stride, size_t frame_stride,
                        cudaStream_t st);
+// tiled tensor map over u8 planes (x, y, frame) with a box_w x box_h x 1 box, zero fill outside;
+// false if the driver has no encoder or the base / strides are not 16-byte aligned
+bool encode_u8_map3d(CUtensorMap* out, const uint8_t* base, uint64_t w, uint64_t h, uint64_t n,
+                     uint64_t row_stride, uint64_t frame_stride, uint32_t box_w, uint32_t box_h);
 int launch_depth_import(const Geom& g, const Pools& p, int n, const int* d_slots,
                         const uint8_t* d_src, size_t row_stride, size_t frame_stride,
                         cudaStream_t st);
