@@ -268,6 +268,8 @@ struct ScatterShared {
   alignas(16) uint32_t sd[kSegRows * kScDerivPitch];   // gx:13 | gy:13 << 13 of every pixel
   alignas(16) uint32_t cm[(kSegRows / 8) * (kStripW / 4)];  // [band][column group]: byte i = 8-row
                                                             // selection mask of column 4*group + i
+  alignas(16) int4 info[2];  // {level, x0, y0, slot} of the tile in each buffer
+  int seg[2];
   alignas(8) uint64_t bar[2];
 };
 struct ScatterMaps {
@@ -355,16 +357,15 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
   ScatterShared& sh = *reinterpret_cast<ScatterShared*>(scatter_smem);
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int total = item_count * n_slots;
-  if (t == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sc_smem_u32(&sh.bar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sc_smem_u32(&sh.bar[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  const int cq = lane & 3, rq = lane >> 2;  // column phase: lane = (row rq, column cq) of a 4 x 8 step
+  // Thread 0 decodes a work item once (level, tile origin, slot), starts its tensor copies and
+  // leaves the result in shared memory; everybody else reads it after the next barrier.
   auto issue = [&](int work, int buf) {  // thread 0 only
     const TileItem it = locate_item(geom, work % item_count + item_begin);
     const int slot = slots[work / item_count];
     const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
+    sh.info[buf] = make_int4(it.lvl, x0, y0, slot);
+    sh.seg[buf] = it.seg;
     // the buffers were read (and the image tile patched) through the generic proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
@@ -374,23 +375,50 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
     sc_tma_load_3d(sh.sg[buf], &maps.g[it.lvl], x0, y0, slot, &sh.bar[buf]);
     sc_tma_load_3d(sh.si[buf], &maps.img[it.lvl], x0 - 16, y0 - 1, slot, &sh.bar[buf]);
   };
+  // Per-tile values that come from global memory -- the integer threshold and the start offsets
+  // of this lane's four (column, segment) runs -- are requested one tile ahead.
+  struct TileRegs {
+    int lvl, x0, y0, slot;
+    uint32_t ithr, base[4];
+  };
+  auto fetch = [&](int buf) {
+    TileRegs r;
+    const int4 in = sh.info[buf];
+    r.lvl = in.x, r.x0 = in.y, r.y0 = in.z, r.slot = in.w;
+    const LevelGeom& L = geom.lv[r.lvl];
+    r.ithr = (uint32_t)__ldg(&pools.ithr[(size_t)r.slot * kMaxLevels + r.lvl]);
+    const uint32_t* cnt = pools.cnt + (size_t)r.slot * geom.cnt_elems + L.cnt_off;
+    const int seg = sh.seg[buf];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int x = r.x0 + (wid * 4 + q) * 4 + cq;
+      r.base[q] = (x < L.w) ? __ldg(&cnt[(size_t)x * L.nseg + seg]) : 0u;
+    }
+    return r;
+  };
   int work = blockIdx.x, buf = 0;
   uint32_t phases = 0u;  // bit b: parity the next wait on bar[b] expects
-  if (work < total && t == 0) issue(work, 0);
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sc_smem_u32(&sh.bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sc_smem_u32(&sh.bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (work < total) issue(work, 0);
+  }
+  __syncthreads();
+  if (work >= total) return;
+  TileRegs cur = fetch(0), nxt = cur;
   for (; work < total; work += gridDim.x, buf ^= 1) {
     const int next = work + gridDim.x;
     if (next < total && t == 0) issue(next, buf ^ 1);
     sc_mbar_wait(&sh.bar[buf], (phases >> buf) & 1u);
     phases ^= 1u << buf;
-    const TileItem it = locate_item(geom, work % item_count + item_begin);
-    const int slot = slots[work / item_count];
-    const LevelGeom& L = geom.lv[it.lvl];
-    const int x0 = it.strip * kStripW, y0 = it.seg * kSegRows;
-    const uint32_t ithr = (uint32_t)pools.ithr[(size_t)slot * kMaxLevels + it.lvl];
+    const LevelGeom& L = geom.lv[cur.lvl];
+    const int x0 = cur.x0, y0 = cur.y0, slot = cur.slot;
+    const uint32_t ithr = cur.ithr;
     const uint8_t* tg = sh.sg[buf];
     uint8_t* ti = sh.si[buf];
-    const uint32_t* cnt = pools.cnt + (size_t)slot * geom.cnt_elems + L.cnt_off;
     uint64_t* rec = pools.rec + (size_t)slot * geom.rec_elems + L.rec_off;
+    asm volatile("" : "+l"(rec));  // keep base + 32-bit index addressing (one IMAD.WIDE per store)
     const bool all_points = kDepth && geom.depth_mode == UWT_DEPTH_ALL_POINTS;
     const uint16_t* dplane = kDepth ? pools.dep + (size_t)slot * geom.plane_elems + L.plane_off
                                     : nullptr;
@@ -444,16 +472,16 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
       sh.cm[band * (kStripW / 4) + lane] = acc;
     }
     __syncthreads();
+    if (next < total) nxt = fetch(buf ^ 1);  // info[buf ^ 1] was written before the barrier above
     // ---- column phase: 4 columns x 8 rows per step ----
     {
-      const int cq = lane & 3, rq = lane >> 2;
       const uint32_t below = (1u << rq) - 1u;
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int cg = wid * 4 + q;           // column group of this step
         const int c = cg * 4 + cq, x = x0 + c;
         if (x0 + cg * 4 >= L.w) break;        // warp-uniform
-        uint32_t base = (x < L.w) ? __ldg(&cnt[(size_t)x * L.nseg + it.seg]) : 0u;
+        uint32_t base = cur.base[q];
         const uint8_t* cmb = reinterpret_cast<const uint8_t*>(sh.cm) + cg * 4 + cq;
         const uint32_t* dcol = sh.sd + rq * kScDerivPitch + c;
         const uint8_t* icol = ti + (rq + 1) * kScImgW + 16 + c;
@@ -461,7 +489,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
 #pragma unroll
         for (int b = 0; b < kSegRows / 8; ++b) {
           const uint32_t m8 = cmb[b * kStripW];
-          bool sel = (m8 >> rq) & 1u;
+          uint32_t sel = (m8 >> rq) & 1u;
           uint32_t o = base + __popc(m8 & below);
           if constexpr (kDepth) {
             // Tracker.cpp:1339: depth != 0 as well.  The count kernel applied the same test, so
@@ -471,7 +499,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
               dz = depth_at(dplane, L.pitch, x, y0 + b * 8 + rq, geom.depth_mode);
               sel = dz != 0;
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, sel);
+            const uint32_t bal = __ballot_sync(0xffffffffu, sel != 0u);
             // lanes of column cq sit at bit positions cq, cq + 4, ...: rows below this lane's
             const uint32_t colbits = bal & (0x11111111u << cq);
             o = base + __popc(colbits & ((1u << lane) - 1u));
@@ -480,15 +508,23 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
           } else {
             base += __popc(m8);
           }
-          if (sel) {
-            const uint32_t i1 = icol[b * 8 * kScImgW];
-            const uint32_t hi = dcol[b * 8 * kScDerivPitch];
-            rec[o] = (uint64_t)(xy | (i1 << 24)) | ((uint64_t)hi << 32);
-          }
+          // branch-free: every lane assembles a record, the selected ones store it
+          const uint32_t i1 = icol[b * 8 * kScImgW];
+          const uint32_t hi = dcol[b * 8 * kScDerivPitch];
+          const uint32_t lo = xy | (i1 << 24);
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ne.u32 p, %0, 0;\n"
+              "@p st.global.v2.u32 [%1], {%2, %3};\n"
+              "}\n" ::"r"(sel),
+              "l"(rec + o), "r"(lo), "r"(hi)
+              : "memory");
           xy += 8u << 12;
         }
       }
     }
+    cur = nxt;
     __syncthreads();  // both buffers of this stage are refilled in the next iteration
   }
 }
