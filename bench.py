@@ -406,7 +406,7 @@ def run_ours(args):
             prev, cur = cur, prev
         barrier()
         t.profile(True)
-        l0 = t.launch_count()
+        l0 = t.launch_count(include_aux=True)
         sampler = ClockSampler(local_rank)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -425,7 +425,7 @@ def run_ours(args):
         clocks = sampler.stop()
         ms_own = e0.elapsed_time(e1)
         prof = t.profile_read()
-        launches = t.launch_count() - l0
+        launches = t.launch_count(include_aux=True) - l0
         t.profile(False)
         ms = ms_own
         if world > 1:
@@ -660,7 +660,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="sequences per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per problem (0 = auto)")
     ap.add_argument("--dmma-accum", action="store_true",
                     help="A/B: Gram accumulator in fp64 DMMA fragments (slower; off by default)")

@@ -298,8 +298,12 @@ int uwt_get_records(uwt_tracker* t, int slot, int level, uint64_t* packed, int c
  * recorded for batches of at most 64 problems; after a larger batch (not traced) the call returns
  * UWT_E_STATE instead of an earlier batch's rows. */
 int uwt_get_trace(uwt_tracker* t, int index, uwt_iter_trace* out, int capacity, int* n);
-/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+/* Number of compute kernels this handle has launched so far. */
 long long uwt_launch_count(const uwt_tracker* t);
+/* Number of argument-staging kernels launched so far: the slot / pose arrays of a call reach the
+ * device through a one-CTA copy kernel (not a host-to-device copy, which would queue behind frame
+ * uploads).  bench.py's gpu_launches = uwt_launch_count + uwt_aux_launch_count. */
+long long uwt_aux_launch_count(const uwt_tracker* t);
 
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's
  * roofline numbers).  Classes: */

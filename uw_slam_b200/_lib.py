@@ -107,6 +107,7 @@ SIGNATURES = {
     "uwt_get_records": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int, _ip]),
     "uwt_get_trace": (C.c_int, [_H, C.c_int, C.POINTER(IterTrace), C.c_int, _ip]),
     "uwt_launch_count": (C.c_longlong, [_H]),
+    "uwt_aux_launch_count": (C.c_longlong, [_H]),
     "uwt_profile_enable": (C.c_int, [_H, C.c_int]),
     "uwt_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }

@@ -42,8 +42,14 @@ struct FlowProblem {  // device-resident state of one problem between tasks
   int lvl, k, n, nchunks, ntrace;
   unsigned done;      // chunks of the current sweep completed so far
   int phase;          // Tukey weights: 1 = histogram pass of the sweep, 0 = accumulation pass
-  int chunk;          // candidate records per task of the current sweep
+  int chunk;          // low 16 bits: candidate records per task of the current sweep / 16;
+                      // high 16 bits: residual sweeps this problem has completed so far
 };
+__device__ __forceinline__ int flow_pack_chunk(int records, int sweeps) {
+  return (records >> 4) | (min(sweeps, 0x7FFF) << 16);
+}
+__device__ __forceinline__ int flow_chunk_of(int packed) { return (packed & 0xFFFF) << 4; }
+__device__ __forceinline__ int flow_sweeps_of(int packed) { return packed >> 16; }
 static_assert(sizeof(FlowProblem) == 64, "FlowProblem is one 64-byte record");
 
 struct FlowCtl {
@@ -182,9 +188,25 @@ struct FlowShared {
 #define UWT_FLOW_MIN_CHUNK 1024
 #endif
 constexpr int kFlowMinChunk = UWT_FLOW_MIN_CHUNK;
-__host__ __device__ inline int flow_chunk_records(int nprob, int grid, int n) {
+// Late sweeps: a problem that has already run kFlowLateSweeps sweeps (the batch's mean is ~11.5
+// on the headline workload) is one of the stragglers the launch ends with -- by then most CTAs
+// have nothing to do, and the latency of a sweep is the time of ONE task.  Its sweeps are cut
+// kFlowLateShift times finer.  The rule reads the problem's own history only, so it is as
+// deterministic as the rest of the partition.
+#ifndef UWT_FLOW_LATE_SWEEPS
+#define UWT_FLOW_LATE_SWEEPS 14
+#endif
+#ifndef UWT_FLOW_LATE_SHIFT
+#define UWT_FLOW_LATE_SHIFT 2
+#endif
+constexpr int kFlowLateSweeps = UWT_FLOW_LATE_SWEEPS, kFlowLateShift = UWT_FLOW_LATE_SHIFT;
+__host__ __device__ inline int flow_chunk_records(int nprob, int grid, int n, int sweeps_done) {
   int c = kFlowChunk;
   while (c > kFlowMinChunk && (long long)nprob * ((n + c - 1) / c) < (long long)grid) c >>= 1;
+  if (sweeps_done >= kFlowLateSweeps) {
+    c >>= kFlowLateShift;
+    if (c < kFlowMinChunk) c = kFlowMinChunk;
+  }
   return c;
 }
 
@@ -197,8 +219,12 @@ __device__ bool flow_enter_level(const Geom& geom, const Pools& pools, const Est
     fp.k = 0;
     fp.last_error = 50000.0f;  // Tracker.cpp:393
     fp.n = (int)pools.ncand[(size_t)prev_slot * kMaxLevels + fp.lvl];
-    fp.chunk = flow_chunk_records(nprob, (int)gridDim.x, fp.n);
-    fp.nchunks = (fp.n + fp.chunk - 1) / fp.chunk;
+    {
+      const int sweeps = flow_sweeps_of(fp.chunk);
+      const int csz = flow_chunk_records(nprob, (int)gridDim.x, fp.n, sweeps);
+      fp.chunk = flow_pack_chunk(csz, sweeps);
+      fp.nchunks = (fp.n + csz - 1) / csz;
+    }
     if (lane == 0 && io.stats) io.stats[prob].n_points[fp.lvl] = fp.n;
     if (fp.n > 0) return false;
     zero_tot[lane] = 0.0;
@@ -221,6 +247,11 @@ __device__ bool flow_advance(const Geom& geom, const Pools& pools, const Estimat
                              int nprob) {
   if (!brk) {
     fp.k += 1;
+    // same level, next sweep: the partition may change once the problem counts as a straggler
+    const int sweeps = flow_sweeps_of(fp.chunk);
+    const int csz = flow_chunk_records(nprob, (int)gridDim.x, fp.n, sweeps);
+    fp.chunk = flow_pack_chunk(csz, sweeps);
+    fp.nchunks = (fp.n + csz - 1) / csz;
     return false;
   }
   if (fp.lvl != 0) fp.pose = se3_scale_level(fp.pose);  // Tracker.cpp:580-590
@@ -371,7 +402,8 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
     const uint16_t* __restrict__ recz =
         kMode == kFlowDepth ? pools.recz + (size_t)prev_slot * geom.rec_elems + L.rec_off
                             : nullptr;
-    const int csz = __ldcg(&P->chunk);
+    const int chunk_word = __ldcg(&P->chunk);
+    const int csz = flow_chunk_of(chunk_word);
     const int lo = chunk * csz, hi = min(n, lo + csz);
     // The chunk's records stream from DRAM (the batch's working set exceeds the L2): ask for all
     // of them now, one 128-byte line per request, so the point loop finds them in the L2; the
@@ -579,7 +611,7 @@ estimate_flow_kernel(const __grid_constant__ Geom geom, const Pools pools, const
         fp.ntrace = __ldcg(&P->ntrace);
         fp.done = 0;
         fp.phase = tukey ? 1 : 0;
-        fp.chunk = csz;
+        fp.chunk = flow_pack_chunk(csz, flow_sweeps_of(chunk_word) + 1);  // this sweep is done
         uwt_iter_trace* tr = (io.trace && fp.ntrace < io.trace_cap)
                                  ? &io.trace[(size_t)prob * io.trace_cap + fp.ntrace]
                                  : nullptr;

@@ -412,8 +412,12 @@ class Tracker:
     def synchronize(self):
         self._check(self._lib.uwt_synchronize(self._h))
 
-    def launch_count(self):
-        return int(self._lib.uwt_launch_count(self._h))
+    def launch_count(self, include_aux=False):
+        """Compute kernels launched so far; with include_aux also the argument-staging kernels."""
+        n = int(self._lib.uwt_launch_count(self._h))
+        if include_aux:
+            n += int(self._lib.uwt_aux_launch_count(self._h))
+        return n
 
     def profile(self, on=True):
         self._check(self._lib.uwt_profile_enable(self._h, 1 if on else 0))
