@@ -200,8 +200,17 @@ constexpr int kFlowMinChunk = UWT_FLOW_MIN_CHUNK;
 #define UWT_FLOW_LATE_SHIFT 2
 #endif
 constexpr int kFlowLateSweeps = UWT_FLOW_LATE_SWEEPS, kFlowLateShift = UWT_FLOW_LATE_SHIFT;
+// Base size: kFlowChunk records; twice that from kFlowWideBatch problems on, where the queue is
+// deep enough that the per-task costs (hand-over, reduction, the barrier skew of a CTA's warps)
+// weigh more than the granularity at the edges of the launch (measured, ms per estimate call,
+// 8192 / 16384 records: 128 problems 0.786 / 0.801, 192: 1.126 / 1.073, 256: 1.441 / 1.378,
+// 512: 2.796 / 2.607).
+#ifndef UWT_FLOW_WIDE_BATCH
+#define UWT_FLOW_WIDE_BATCH 192
+#endif
+constexpr int kFlowWideBatch = UWT_FLOW_WIDE_BATCH;
 __host__ __device__ inline int flow_chunk_records(int nprob, int grid, int n, int sweeps_done) {
-  int c = kFlowChunk;
+  int c = nprob >= kFlowWideBatch ? 2 * kFlowChunk : kFlowChunk;
   while (c > kFlowMinChunk && (long long)nprob * ((n + c - 1) / c) < (long long)grid) c >>= 1;
   if (sweeps_done >= kFlowLateSweeps) {
     c >>= kFlowLateShift;
