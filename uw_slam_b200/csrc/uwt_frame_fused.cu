@@ -143,24 +143,25 @@ __device__ __forceinline__ uint32_t gradient1(const uint8_t* c, int pitch) {
   return (uint32_t)((s >> 1) + ((s & 1) & ((s >> 1) & 1)));
 }
 
-// 2x2 reduction of a shared-memory region into the next level's region, 4 outputs per item.
-__device__ __forceinline__ void down4(const uint8_t* src, int spitch, uint8_t* dst, int dpitch,
-                                      int dsize, int t) {
-  const int groups = dsize / 4;  // dsize is a multiple of 4 (80, 40, 20)
-  for (int i = t; i < dsize * groups; i += 256) {
-    const int r = i / groups, c = (i % groups) * 4;
-    const uint2 a = *reinterpret_cast<const uint2*>(src + (2 * r) * spitch + 2 * c);
-    const uint2 b = *reinterpret_cast<const uint2*>(src + (2 * r + 1) * spitch + 2 * c);
-    uint32_t out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t aw = (k < 2) ? a.x : a.y, bw = (k < 2) ? b.x : b.y;
-      const int sh = (k & 1) * 16;
-      const uint32_t s = ((aw >> sh) & 0xFF) + ((aw >> (sh + 8)) & 0xFF) + ((bw >> sh) & 0xFF) +
-                         ((bw >> (sh + 8)) & 0xFF) + 2;
-      out |= (s >> 2) << (8 * k);
-    }
-    *reinterpret_cast<uint32_t*>(dst + r * dpitch + c) = out;
+// 2x2 reduction of a shared-memory region into the next level's region, 4 outputs per item
+// (System.cpp:246-251: (a + b + c + d + 2) >> 2), two outputs per register: the even and the odd
+// bytes of a word are spread into 16-bit lanes with one byte permute each, so a word's two
+// horizontal pair sums are one add, the vertical sum and the rounding constant a 3-input add,
+// and no lane can carry into its neighbour (4 * 255 + 2 < 2^16).
+__device__ __forceinline__ uint32_t pair_sums(uint32_t x) {
+  return __byte_perm(x, 0u, 0x4240) + __byte_perm(x, 0u, 0x4341);  // (b0 + b1) | (b2 + b3) << 16
+}
+template <int kDSize>
+__device__ __forceinline__ void down4(const uint8_t* src, uint8_t* dst, int t) {
+  constexpr int kSPitch = 2 * kDSize, kGroups = kDSize / 4;  // kDSize is a multiple of 4
+  for (int i = t; i < kDSize * kGroups; i += 256) {
+    const int r = i / kGroups, c = (i % kGroups) * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(src + (2 * r) * kSPitch + 2 * c);
+    const uint2 b = *reinterpret_cast<const uint2*>(src + (2 * r + 1) * kSPitch + 2 * c);
+    const uint32_t s0 = pair_sums(a.x) + pair_sums(b.x) + 0x00020002u;
+    const uint32_t s1 = pair_sums(a.y) + pair_sums(b.y) + 0x00020002u;
+    // outputs 0, 1 sit in bytes 0, 2 of (s0 >> 2), outputs 2, 3 in bytes 0, 2 of (s1 >> 2)
+    *reinterpret_cast<uint32_t*>(dst + r * kDSize + c) = __byte_perm(s0 >> 2, s1 >> 2, 0x6420);
   }
 }
 
@@ -220,18 +221,24 @@ __device__ __forceinline__ uint32_t level_pass_packed(const uint8_t* reg, const 
   const uint8_t* trow = reg + (kOff + band * kRows - 1) * kSize;  // region row of image row yb-1
   RowWin top = row_windows(trow, sx);
   RowWin mid = row_windows(trow + kSize, sx);
+  // running store addresses (one 64-bit add per row instead of a multiply-add per store); rows of
+  // the band below the image bottom are cut off by the trip count
+  const size_t o0 = (size_t)yb * L.pitch + xg;
+  uint8_t* gp = g_plane + o0;
+  uint8_t* ip = img_plane + o0;
+  const int rows = min(kRows, L.h - yb);
 #pragma unroll
   for (int j = 0; j < kRows; ++j) {
-    const int y = yb + j;
-    if (y >= L.h) break;
+    if (j >= rows) break;
     const RowWin bot = row_windows(trow + (j + 2) * kSize, sx);
-    const uint32_t gq = gradient4<kSobel>(top, mid, bot);
-    gsum = __dp4a(gq & vmask, 0x01010101u, gsum);
-    const size_t o = (size_t)y * L.pitch + xg;
+    const uint32_t gq = gradient4<kSobel>(top, mid, bot) & vmask;
+    gsum = __dp4a(gq, 0x01010101u, gsum);
     // the row pitch is a multiple of 16 and xg of 4: a 4-byte store never leaves the row; bytes
-    // beyond the image width land in the pitch padding, which must stay zero -> mask them
-    *reinterpret_cast<uint32_t*>(g_plane + o) = gq & vmask;
-    if (store_img) *reinterpret_cast<uint32_t*>(img_plane + o) = mid.w[1] & vmask;
+    // beyond the image width land in the pitch padding, which must stay zero -> masked
+    *reinterpret_cast<uint32_t*>(gp) = gq;
+    if (store_img) *reinterpret_cast<uint32_t*>(ip) = mid.w[1] & vmask;
+    gp += L.pitch;
+    ip += L.pitch;
     top = mid;
     mid = bot;
   }
@@ -282,11 +289,11 @@ frame_fused_kernel(const __grid_constant__ Geom geom, const Pools pools,
   mbar_wait(&sh.bar, 0);
 
   // ---- pyramid regions, all in shared memory (System.cpp:246-251) ----
-  if (levels > 1) down4(sh.s0, kF0, sh.s1, kF0 / 2, kF0 / 2, t);
+  if (levels > 1) down4<kF0 / 2>(sh.s0, sh.s1, t);
   __syncthreads();
-  if (levels > 2) down4(sh.s1, kF0 / 2, sh.s2, kF0 / 4, kF0 / 4, t);
+  if (levels > 2) down4<kF0 / 4>(sh.s1, sh.s2, t);
   __syncthreads();
-  if (levels > 3) down4(sh.s2, kF0 / 4, sh.s3, kF0 / 8, kF0 / 8, t);
+  if (levels > 3) down4<kF0 / 8>(sh.s2, sh.s3, t);
   __syncthreads();
   if (levels > 4) {
     constexpr int kS = kF0 / 16, kP = kF0 / 8;
