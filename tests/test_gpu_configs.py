@@ -255,3 +255,43 @@ def test_points_outside_the_division_window(oracle, batch):
         assert [(x.level, x.k, x.n_valid, x.sum_r2) for x in tr] == \
             [(y.level, y.k, y.n_valid, y.sum_r2) for y in otr], i
     t.close()
+
+
+@pytest.mark.parametrize("w,h,levels,first,last,thr", [
+    (1008, 496, 5, 4, 1, 20.0),    # level widths 504 / 252 / 126 / 63: 3-, 2- and 3-pixel tail groups
+    (1008, 496, 5, 4, 0, 0.0),     # level 0 has records too; threshold = mean: about half the pixels
+    (272, 144, 4, 3, 1, 20.0),     # 136 / 68 / 34 columns: one strip and an 8-column second strip
+    (2064, 80, 3, 2, 1, 5.0),      # 1032 columns = 8 strips + 8 columns, 40 rows < one segment
+    (48, 1040, 3, 2, 0, 20.0),     # tall and narrow: 17 row segments, one partial strip
+])
+def test_candidate_scatter_tile_edges(oracle, w, h, levels, first, last, thr):
+    """The scatter kernel's tiles (128 columns x 64 rows staged by tensor copies, dense stencil
+    phase on 4-pixel groups, column walk on 8-row masks) against ObtainCandidatePoints on frames
+    whose level sizes are not multiples of the tile, of 4 pixels or of 8 rows: white noise, so
+    every border, saturation and partial-group path selects something."""
+    import uw_slam_b200 as U
+    rng = np.random.default_rng(w * 7 + h)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    img[:, : w // 3] //= 4      # a flatter region, so that selection is not uniform
+    fx, fy, cx, cy = 0.8 * w, 0.82 * w, w / 2 - 0.5, h / 2 - 0.5
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=3, levels=levels, first_level=first, last_level=last,
+                        gradient_threshold=thr)
+    # slot 2 (not 0): the per-slot offsets of the tensor maps are part of what is tested
+    f = t.AddFrames([2], img)[0]
+    t.ApplyGradient(f)
+    t.ObtainCandidatePoints(f)
+    ref = oracle.FrameData(img, levels=levels, gradient_threshold=thr)
+    for lvl in range(levels):
+        c = f.candidatePoints(lvl)
+        assert c.shape == ref.cand[lvl].shape, (lvl, c.shape, ref.cand[lvl].shape)
+        assert np.array_equal(c, ref.cand[lvl]), lvl
+        if last <= lvl <= first:
+            r = t.get_records(f.slot, lvl)
+            xs, ys = ref.cand[lvl][:, 0].astype(int), ref.cand[lvl][:, 1].astype(int)
+            assert np.array_equal(r["x"], xs) and np.array_equal(r["y"], ys), lvl
+            assert np.array_equal(r["i1"], ref.images[lvl][ys, xs]), lvl
+            assert np.array_equal(r["gx"], ref.gx[lvl][ys, xs]), lvl
+            assert np.array_equal(r["gy"], ref.gy[lvl][ys, xs]), lvl
+    t.close()
