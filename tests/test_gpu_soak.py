@@ -29,7 +29,11 @@ def test_short_parity_soak(tmp_path):
 
 def test_committed_soak_records_are_clean():
     """CPU: the committed long-run records say what the docs say."""
-    for name, tracks in (("parity_soak.json", 100032), ("parity_soak_r02_final.json", 20032)):
+    for name, tracks in (("parity_soak.json", 100032), ("parity_soak_r02_final.json", 20032),
+                         # the end-of-round kernels (16384-record tasks, late-sweep rule, rewritten
+                         # scatter): every sweep at 64 problems per call, final poses at 256
+                         ("parity_soak_r02s_traced.json", 8192),
+                         ("parity_soak_r02s_batch256.json", 16384)):
         with open(os.path.join(ROOT, "profiles", name)) as f:
             j = json.load(f)
         assert j["tracks"] == tracks and j["sweeps"] > 10 * tracks
