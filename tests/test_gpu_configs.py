@@ -295,3 +295,37 @@ def test_candidate_scatter_tile_edges(oracle, w, h, levels, first, last, thr):
             assert np.array_equal(r["gx"], ref.gx[lvl][ys, xs]), lvl
             assert np.array_equal(r["gy"], ref.gy[lvl][ys, xs]), lvl
     t.close()
+
+
+def test_large_frames_stay_on_the_dataflow_kernel_beyond_296_problems(oracle):
+    """320 problems of 1024x640 (finest optimised level 512x320 = 160 k pixels) in ONE call: the
+    batch is served by the dataflow kernel (two launches: ring init + persistent kernel) with
+    16384-record tasks, not by one-CTA clusters; 8 distinct pairs replicated 40 times must give
+    40 identical copies of the oracle's 8 poses."""
+    import uw_slam_b200 as U
+    w, h = 1024, 640
+    fx, fy, cx, cy = 0.8 * w, 0.82 * w, w / 2 - 0.5, h / 2 - 0.5
+    synth.CALIB["_big"] = (w, h, fx, fy, cx, cy)
+    distinct, copies = 8, 40
+    pairs = [synth.render_pair("_big", 300 + i)[:2] for i in range(distinct)]
+    n = distinct * copies
+    t = U.Tracker(False)
+    t.InitializePyramid(w, h, U.CameraModel.from_intrinsics(w, h, fx, fy, cx, cy).GetK(),
+                        max_frames=2 * n)
+    prev = np.stack([pairs[i % distinct][0] for i in range(n)])
+    cur = np.stack([pairs[i % distinct][1] for i in range(n)])
+    fp = t.AddFrames(list(range(n)), prev)
+    fc = t.AddFrames(list(range(n, 2 * n)), cur)
+    t.ApplyGradient(fp)
+    t.ObtainCandidatePoints(fp)
+    l0 = t.launch_count()
+    poses, stats = t.EstimatePose(fp, fc, return_stats=True)
+    assert t.launch_count() - l0 == 2        # flow_init_kernel + estimate_flow_kernel
+    p = oracle.default_params(w, h, fx, fy, cx, cy)
+    for i in range(distinct):
+        opose, ostats, _ = oracle.estimate_pose(p, oracle.FrameData(pairs[i][0]),
+                                                oracle.FrameData(pairs[i][1], with_candidates=False))
+        for c in range(copies):
+            assert np.array_equal(poses[i + c * distinct], opose), (i, c)
+            assert list(stats[i + c * distinct].evaluations)[:5] == list(ostats.evaluations)[:5]
+    t.close()
