@@ -174,18 +174,16 @@ cand_count_kernel(const __grid_constant__ Geom geom, const Pools pools,
       } else {
         // depth branch (Tracker.cpp:1339): a pixel counts only if its depth is non-zero too
         const uint16_t* dplane = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off;
+        const uint32_t vm = valid4(gx, L.w);
+        uint32_t nz[kRowsPerWarp];
 #pragma unroll
-        for (int r = 0; r < kRowsPerWarp; ++r) {
+        for (int r = 0; r < kRowsPerWarp; ++r) {  // one vector load per row, all in flight
           const int gy = y0 + wid * kRowsPerWarp + r;
-          uint32_t nz = 0;
-          if (gy < L.h) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (gx + i < L.w && depth_at(dplane, L.pitch, gx + i, gy, geom.depth_mode) != 0)
-                nz |= 1u << (8 * i);
-          }
-          acc += (all ? 0x01010101u : __vsetgtu4(w[r], thr4)) & nz;
+          nz[r] = (gy < L.h) ? depth_nz4(dplane + (size_t)gy * L.pitch, gx, geom.depth_mode) : 0u;
         }
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r)
+          acc += (all ? 0x01010101u : __vsetgtu4(w[r], thr4)) & nz[r] & vm;
       }
     }
     part[wid][lane] = acc;
@@ -445,6 +443,31 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
           mw[3] = __funnelshift_r(c1, r1, 16);
         }
         const uint32_t thr4 = min(ithr, 255u) * 0x01010101u;
+        // Tracker.cpp:1339: depth != 0 as well.  The depth test of the band's 8 rows is requested
+        // up front (8 independent vector loads, one latency) and folded into the selection mask,
+        // so the column phase is the same as without depth.
+        uint32_t nzr[8];
+        if constexpr (kDepth) {
+          // rows below the image bottom are clamped (their selection bits are cleared anyway);
+          // the mode is tested once, outside the loads
+          const uint32_t r0 = (uint32_t)(y0 + band * 8), rmax = (uint32_t)(L.h - 1);
+          if (geom.depth_mode == UWT_DEPTH_REFERENCE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              nzr[j] = depth_nz4(dplane + min(r0 + j, rmax) * (uint32_t)L.pitch, xg,
+                                 UWT_DEPTH_REFERENCE);
+          } else if (geom.depth_mode == UWT_DEPTH_ALL_POINTS) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              nzr[j] = depth_nz4(dplane + min(r0 + j, rmax) * (uint32_t)L.pitch, xg,
+                                 UWT_DEPTH_ALL_POINTS);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              nzr[j] = depth_nz4(dplane + min(r0 + j, rmax) * (uint32_t)L.pitch, xg,
+                                 UWT_DEPTH_U16);
+          }
+        }
         // bytes of the group beyond the image width never count (all-points mode has no
         // gradient test; elsewhere their gradient is zero anyway)
         const int nvalid = min(4, L.w - xg);
@@ -466,6 +489,7 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
           out[j * (kScDerivPitch / 4)] = make_uint4(d[0], d[1], d[2], d[3]);
           uint32_t sel4 = all_points ? 0x01010101u : __vsetgtu4(gr[j * (kStripW / 4)], thr4);
           if (y0 + band * 8 + j >= L.h) sel4 = 0u;
+          if constexpr (kDepth) sel4 &= nzr[j];
           acc |= (sel4 & vmask) << j;
         }
       }
@@ -486,27 +510,38 @@ cand_scatter_kernel(const __grid_constant__ Geom geom, const Pools pools,
         const uint32_t* dcol = sh.sd + rq * kScDerivPitch + c;
         const uint8_t* icol = ti + (rq + 1) * kScImgW + 16 + c;
         uint32_t xy = (uint32_t)x | ((uint32_t)(y0 + rq) << 12);
+        // depth of a record (depth modes): this lane's column of the depth plane.  REFERENCE mode
+        // reads byte x of the 16-bit row (Tracker.cpp:1344 at<uchar>); a selected pixel has passed
+        // the depth test, so ALL_POINTS needs no sign check here.
+        const uint16_t* dlane = nullptr;
+        uint32_t dshift = 0, dmask = 0xFFFFu;
+        if constexpr (kDepth) {
+          const int xx = min(x, L.w - 1);
+          const bool ref = geom.depth_mode == UWT_DEPTH_REFERENCE;
+          dlane = dplane + (ref ? (xx >> 1) : xx);
+          dshift = (ref && (xx & 1)) ? 8u : 0u;
+          dmask = ref ? 0xFFu : 0xFFFFu;
+        }
 #pragma unroll
         for (int b = 0; b < kSegRows / 8; ++b) {
           const uint32_t m8 = cmb[b * kStripW];
           uint32_t sel = (m8 >> rq) & 1u;
           uint32_t o = base + __popc(m8 & below);
+          base += __popc(m8);
           if constexpr (kDepth) {
-            // Tracker.cpp:1339: depth != 0 as well.  The count kernel applied the same test, so
-            // the offsets come from a ballot over the pixels that pass both.
-            int dz = 0;
-            if (sel) {
-              dz = depth_at(dplane, L.pitch, x, y0 + b * 8 + rq, geom.depth_mode);
-              sel = dz != 0;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, sel != 0u);
-            // lanes of column cq sit at bit positions cq, cq + 4, ...: rows below this lane's
-            const uint32_t colbits = bal & (0x11111111u << cq);
-            o = base + __popc(colbits & ((1u << lane) - 1u));
-            if (sel) recz[o] = (uint16_t)dz;
-            base += __popc(colbits);
-          } else {
-            base += __popc(m8);
+            // the integer depth of a selected pixel travels next to its record: loaded by every
+            // lane (clamped into the image, so the 8 loads of a column group pipeline), stored by
+            // the selected ones
+            const uint32_t yy = min((uint32_t)(y0 + b * 8 + rq), (uint32_t)(L.h - 1));
+            const uint32_t dz = ((uint32_t)__ldg(dlane + yy * (uint32_t)L.pitch) >> dshift) & dmask;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ne.u32 p, %0, 0;\n"
+                "@p st.global.u16 [%1], %2;\n"
+                "}\n" ::"r"(sel),
+                "l"(recz + o), "h"((unsigned short)dz)
+                : "memory");
           }
           // branch-free: every lane assembles a record, the selected ones store it
           const uint32_t i1 = icol[b * 8 * kScImgW];
@@ -577,18 +612,15 @@ cand_mask_kernel(const __grid_constant__ Geom geom, const Pools pools,
       const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t m = all ? 0x01010101u : __vsetgtu4(w8[j], thr4);  // 0 / 1 per byte
-        word |= ((m * 0x01020408u) >> 24) << (4 * j);          // -> 4 bits
-      }
-      if constexpr (kDepth) {  // Tracker.cpp:1339: depth != 0 as well
-        const uint16_t* dplane = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off;
-        uint32_t rest = word;
-        while (rest) {
-          const int bit = __ffs(rest) - 1;
-          rest &= rest - 1;
-          if (x0 + bit >= L.w || depth_at(dplane, L.pitch, x0 + bit, row, geom.depth_mode) == 0)
-            word &= ~(1u << bit);
+        uint32_t m = all ? 0x01010101u : __vsetgtu4(w8[j], thr4);  // 0 / 1 per byte
+        if constexpr (kDepth) {  // Tracker.cpp:1339: depth != 0 as well, 4 pixels per load
+          const uint16_t* drow = pools.dep + (size_t)slot * geom.plane_elems + L.plane_off +
+                                 (size_t)row * L.pitch;
+          const int gx = x0 + 4 * j;
+          m &= valid4(gx, L.w);
+          if (m) m &= depth_nz4(drow, gx, geom.depth_mode);
         }
+        word |= ((m * 0x01020408u) >> 24) << (4 * j);          // -> 4 bits
       }
     }
     pools.sel_mask[(size_t)slot * geom.mask_elems + L.mask_off + idx] = word;

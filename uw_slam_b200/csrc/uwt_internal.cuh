@@ -118,6 +118,37 @@ __device__ __forceinline__ int depth_at(const uint16_t* __restrict__ plane, int 
   return (int)plane[(size_t)y * pitch + x];
 }
 
+// The depth test of ObtainCandidatePoints / ObtainAllPoints (depth_at(..) != 0) for the 4 pixels
+// gx .. gx + 3 of one depth row (gx a multiple of 4, gx < pitch) from ONE vector load: 0 / 1 per
+// byte.  Pixels beyond the image width are the caller's business (valid4).
+__device__ __forceinline__ uint32_t depth_nz4(const uint16_t* __restrict__ row, int gx,
+                                              int depth_mode) {
+  if (depth_mode == UWT_DEPTH_REFERENCE) {
+    // at<uchar>(y, x) on the CV_16U image: byte x of the row
+    const uint32_t v = __ldg(
+        reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(row) + gx));
+    return ((v | ((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) >> 7) & 0x01010101u;
+  }
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + gx));
+  const bool positive = depth_mode == UWT_DEPTH_ALL_POINTS;  // at<short>(y, x) > 0
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t w = k ? v.y : v.x;
+    // bit 15 / 31 of (w | ((w & 0x7FFF..) + 0x7FFF..)): the halfword is non-zero
+    uint32_t t = (w | ((w & 0x7FFF7FFFu) + 0x7FFF7FFFu)) >> 15;
+    if (positive) t &= ~(w >> 15);  // sign bit clear
+    t &= 0x00010001u;
+    out |= ((t | (t >> 8)) & 0x0101u) << (16 * k);
+  }
+  return out;
+}
+// 0x01 in the bytes of the pixels gx .. gx + 3 that lie inside an image of width w
+__device__ __forceinline__ uint32_t valid4(int gx, int w) {
+  const int n = w - gx;
+  return n >= 4 ? 0x01010101u : (n <= 0 ? 0u : (0x01010101u >> (8 * (4 - n))));
+}
+
 struct EstimateIO {
   const int* prev_slots;
   const int* cur_slots;
