@@ -255,7 +255,10 @@ int uwt_fetch_poses(uwt_tracker* t, int n, float* out_poses7, uwt_track_stats* s
  *     uwt_shard_update(t, d_sums, &done);       // break test, solve, update -- identical
  *                                               // on every rank, no broadcast needed
  * until done != 0, then uwt_shard_result.  d_sums32: 32 doubles in DEVICE memory owned by the
- * caller (layout: 21 upper-triangular J^T J terms, 6 J^T r terms, sum r^2, N_valid, 3 pad). */
+ * caller (layout: 21 upper-triangular J^T J terms, 6 J^T r terms, sum r^2, N_valid, the weighted
+ * error term r^T W r of the Huber mode, 2 pad).  Weights: identity or Huber (a fixed function of
+ * the integer residual: every rank builds the same tables); Tukey / MAD weights depend on the
+ * sweep's residual histogram over ALL ranks and are rejected here (UWT_E_INVALID). */
 int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int nranks,
                     const float* init_pose7);
 int uwt_shard_accumulate(uwt_tracker* t, double* d_sums32);

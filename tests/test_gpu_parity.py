@@ -504,6 +504,62 @@ def test_fused_sharded_two_emulated_ranks_match_oracle(oracle, pairs):
         t.close()
 
 
+def test_sharded_mode_huber_weights_match_oracle(oracle, pairs):
+    """Huber weights in the sharded mode (both forms): the weight is a fixed function of the
+    integer residual, so every rank builds the same tables and the 32 exchanged sums carry the
+    weighted error term.  Two emulated ranks per form against the oracle with the same weights;
+    Tukey / MAD weights (a histogram all-reduce per sweep) stay rejected."""
+    torch = pytest.importorskip("torch")
+    import uw_slam_b200 as U
+    import uw_slam_b200._lib as L
+    calib = "euroc"
+    w, h, fx, fy, cx, cy = synth.CALIB[calib]
+    prev, cur = pairs(calib, 6)
+    cur = cur.copy()
+    cur[100:220, 300:520] = 255          # an occluder: the weights must matter
+    rp, rc = oracle.FrameData(prev), oracle.FrameData(cur, with_candidates=False)
+    opose, _, _ = oracle.estimate_pose(
+        oracle.default_params(w, h, fx, fy, cx, cy, weight_mode=2, huber_delta=6.0), rp, rc)
+    ident, _, _ = oracle.estimate_pose(oracle.default_params(w, h, fx, fy, cx, cy), rp, rc)
+    assert not np.array_equal(opose, ident)
+    ts = [make_tracker(calib, weight_mode=L.WEIGHT_HUBER, huber_delta=6.0) for _ in range(2)]
+    for t in ts:
+        fp, fc = t.AddFrames([0, 1], np.stack([prev, cur]))
+        t.ApplyGradient(fp)
+        t.ObtainCandidatePoints(fp)
+    # NCCL-form kernels, the all-reduce played by a torch sum
+    sums = [torch.zeros(32, dtype=torch.float64, device="cuda") for _ in ts]
+    for r, t in enumerate(ts):
+        t.ShardBegin(0, 1, r, 2)
+    for _ in range(400):
+        for r, t in enumerate(ts):
+            t.ShardAccumulate(sums[r].data_ptr())
+            t.synchronize()
+        total = torch.stack(sums).sum(0)
+        torch.cuda.synchronize()
+        done = [t.ShardUpdate(total.data_ptr()) for t in ts]
+        if done[0]:
+            break
+    for t in ts:
+        assert np.array_equal(t.ShardResult()[0], opose)
+    # fused form: peer mailboxes
+    for r, t in enumerate(ts):
+        t.ShardConnectLocal(r, ts)
+    for t in ts:
+        t.ShardEstimateFusedAsync(0, 1, grid=64)
+    poses = [t.ShardEstimateFusedWait()[0] for t in ts]
+    assert np.array_equal(poses[0], opose) and np.array_equal(poses[1], opose)
+    for t in ts:
+        t.close()
+    tk = make_tracker(calib, weight_mode=L.WEIGHT_TUKEY)
+    fp, fc = tk.AddFrames([0, 1], np.stack([prev, cur]))
+    tk.ApplyGradient(fp)
+    tk.ObtainCandidatePoints(fp)
+    with pytest.raises(U.UwtError):
+        tk.ShardBegin(0, 1, 0, 1)
+    tk.close()
+
+
 def test_two_devices_in_one_process(oracle, pairs):
     """Handles on different GPUs of one process (function attributes are per device): both must
     track, on every estimate kernel.  Needs >= 2 visible GPUs."""

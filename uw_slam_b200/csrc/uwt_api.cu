@@ -1151,10 +1151,11 @@ int uwt_shard_begin(uwt_tracker* t, int prev_slot, int cur_slot, int rank, int n
   if ((rc = check_slots(t, 1, &cur_slot))) return rc;
   if (nranks < 1 || rank < 0 || rank >= nranks)
     return fail(t, UWT_E_INVALID, "bad shard rank %d of %d", rank, nranks);
-  if (t->cfg.weight_mode != UWT_WEIGHT_IDENTITY || t->cfg.depth_mode != UWT_DEPTH_NONE ||
+  if (t->cfg.weight_mode == UWT_WEIGHT_TUKEY || t->cfg.depth_mode != UWT_DEPTH_NONE ||
       t->cfg.sampling != UWT_SAMPLE_NEAREST)
     return fail(t, UWT_E_INVALID,
-                "the sharded mode supports identity weights, mono input, nearest sampling only");
+                "the sharded mode supports identity or Huber weights, mono input, nearest "
+                "sampling only (Tukey/MAD weights need the sweep's residual histogram)");
   if (!t->slots[prev_slot].candidates)
     return fail(t, UWT_E_STATE, "prev slot %d has no candidate points", prev_slot);
   if (!t->slots[cur_slot].pyramid) return fail(t, UWT_E_STATE, "cur slot %d has no frame", cur_slot);

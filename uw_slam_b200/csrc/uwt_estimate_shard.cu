@@ -15,6 +15,36 @@ namespace uwt {
 // ----------------------------------------------------------------------------------------
 constexpr int kShardThreads = 256;
 
+// Huber weights (UWT_WEIGHT_HUBER, ARITHMETIC.md R4) in the sharded mode: the weight of a point is
+// a fixed function of its integer residual, so every rank builds the same three tables and the
+// exchange stays the 32 sums of the identity case (sum 29 carries the weighted error term).
+// Tukey / MAD weights would need the sweep's residual histogram all-reduced first: not offered.
+template <bool kWeighted>
+struct ShardLut {
+  float s[kWeighted ? 512 : 1], rs[kWeighted ? 512 : 1], e[kWeighted ? 512 : 1];
+};
+template <bool kWeighted>
+__device__ __forceinline__ WeightLut shard_build_lut(ShardLut<kWeighted>& t, const Geom& geom,
+                                                     float rscale, int tid) {
+  WeightLut lut = {};
+  if constexpr (kWeighted) {
+    for (int i = tid; i < 512; i += kShardThreads) {
+      const float r = (float)(i - 255);
+      const float a = fabsf(r);
+      const float w = (a <= geom.huber_delta) ? 1.0f : __fdiv_rn(geom.huber_delta, a);
+      const float sq = __fsqrt_rn(w);
+      t.s[i] = sq;
+      t.rs[i] = __fmul_rn(__fmul_rn(r, rscale), sq);
+      t.e[i] = __fmul_rn(r, w);
+    }
+    lut.s = t.s;
+    lut.rs = t.rs;
+    lut.e = t.e;
+  }
+  return lut;
+}
+
+template <bool kWeighted>
 __global__ void __launch_bounds__(kShardThreads, 2)
 shard_accumulate_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardState* st,
                         double* __restrict__ partials, double* __restrict__ out32, int table_w,
@@ -24,6 +54,7 @@ shard_accumulate_kernel(const __grid_constant__ Geom geom, const Pools pools, Sh
   double* const tab_y = tab_x + 3 * table_w;
   __shared__ double warp_part[kShardThreads / 32][kNQ];
   __shared__ int is_last;
+  __shared__ ShardLut<kWeighted> lut_mem;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int lvl = st->level;
   DPose pose;
@@ -43,6 +74,7 @@ shard_accumulate_kernel(const __grid_constant__ Geom geom, const Pools pools, Sh
   const float rscale = geom.residual_scale;
   const bool rscale_is_int = (rscale == truncf(rscale)) && fabsf(rscale) <= 32768.0f;
   const int rscale_i = rscale_is_int ? (int)rscale : 0;
+  const WeightLut lut = shard_build_lut<kWeighted>(lut_mem, geom, rscale, tid);
   build_tables(pose, L, tab_x, table_w, tab_y, table_h, tid, kShardThreads);
   __syncthreads();
   double acc[kNQ];
@@ -56,8 +88,8 @@ shard_accumulate_kernel(const __grid_constant__ Geom geom, const Pools pools, Sh
     while (i < hi) {
       const int inext = i + stride;
       const uint64_t rec_next = (inext < hi) ? __ldg(&recs[inext]) : 0ull;
-      accumulate_point<false>(wc, rec, tab_x, table_w, tab_y, table_h, I2, rscale, rscale_is_int,
-                              rscale_i, acc, sum_r2, n_val, WeightLut{});
+      accumulate_point<kWeighted>(wc, rec, tab_x, table_w, tab_y, table_h, I2, rscale,
+                                  rscale_is_int, rscale_i, acc, sum_r2, n_val, lut);
       rec = rec_next;
       i = inext;
     }
@@ -126,9 +158,16 @@ int launch_shard_accumulate(const Geom& g, const Pools& p, ShardState* st, doubl
                             double* out32, int grid, cudaStream_t stream) {
   const int tw = g.lv[g.last_level].w, th = g.lv[g.last_level].h;
   const size_t smem = sizeof(double) * 3 * (size_t)(tw + th);
-  static size_t smem_cache[kMaxDevices];  // one per kernel instantiation and device
-  if (!ensure_dynamic_smem(shard_accumulate_kernel, smem, smem_cache)) return -1;
-  shard_accumulate_kernel<<<grid, kShardThreads, smem, stream>>>(g, p, st, partials, out32, tw, th);
+  static size_t smem_cache[2][kMaxDevices];  // one per kernel instantiation and device
+  if (g.weight_mode == UWT_WEIGHT_HUBER) {
+    if (!ensure_dynamic_smem(shard_accumulate_kernel<true>, smem, smem_cache[1])) return -1;
+    shard_accumulate_kernel<true><<<grid, kShardThreads, smem, stream>>>(g, p, st, partials, out32,
+                                                                         tw, th);
+  } else {
+    if (!ensure_dynamic_smem(shard_accumulate_kernel<false>, smem, smem_cache[0])) return -1;
+    shard_accumulate_kernel<false><<<grid, kShardThreads, smem, stream>>>(g, p, st, partials,
+                                                                          out32, tw, th);
+  }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -151,6 +190,7 @@ int launch_shard_update(const Geom& g, const Pools& p, ShardState* st, const dou
 
 constexpr long long kSpinLimit = 50LL * 1000 * 1000;  // x (20 ns sleep + one load): seconds
 
+template <bool kWeighted>
 __global__ void __launch_bounds__(kShardThreads, 2)
 shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardState* st,
                    ShardFused* ctl, ShardMailbox* mine, double* __restrict__ partials,
@@ -164,11 +204,13 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
   __shared__ int s_level, s_done;
   __shared__ float s_pose[7];
   __shared__ int s_ncand[kMaxLevels];
+  __shared__ ShardLut<kWeighted> lut_mem;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int rank = st->rank, nranks = st->nranks;
   const float rscale = geom.residual_scale;
   const bool rscale_is_int = (rscale == truncf(rscale)) && fabsf(rscale) <= 32768.0f;
   const int rscale_i = rscale_is_int ? (int)rscale : 0;
+  const WeightLut lut = shard_build_lut<kWeighted>(lut_mem, geom, rscale, tid);  // before the first barrier
   const unsigned gen0 = ctl->generation;             // same value in every CTA at launch
   const unsigned long long seq0 = ctl->seq;
   unsigned local_sweep = 0;
@@ -228,19 +270,19 @@ shard_fused_kernel(const __grid_constant__ Geom geom, const Pools pools, ShardSt
         const uint32_t ax = (uint32_t)__cvta_generic_to_shared(tab_x) - (uint32_t)xlo * 8u;
         const uint32_t ay = (uint32_t)__cvta_generic_to_shared(tab_y);
         if (table_w == 1024)
-          fast_sweep<false, 1024>(geom, lvl, recs, first, chi, stride, rec0, rec1, ax, ay,
-                                  tab_x - xlo, tab_y, I2, rscale, acc, sum_r2, n_val, WeightLut{});
+          fast_sweep<kWeighted, 1024>(geom, lvl, recs, first, chi, stride, rec0, rec1, ax, ay,
+                                      tab_x - xlo, tab_y, I2, rscale, acc, sum_r2, n_val, lut);
         else
-          fast_sweep<false, 2048>(geom, lvl, recs, first, chi, stride, rec0, rec1, ax, ay,
-                                  tab_x - xlo, tab_y, I2, rscale, acc, sum_r2, n_val, WeightLut{});
+          fast_sweep<kWeighted, 2048>(geom, lvl, recs, first, chi, stride, rec0, rec1, ax, ay,
+                                      tab_x - xlo, tab_y, I2, rscale, acc, sum_r2, n_val, lut);
       } else {
         int i = first;
         uint64_t rec = (i < chi) ? __ldg(&recs[i]) : 0ull;
         while (i < chi) {
           const int inext = i + stride;
           const uint64_t rec_next = (inext < chi) ? __ldg(&recs[inext]) : 0ull;
-          accumulate_point<false>(wc, rec, tab_x - xlo, table_w, tab_y, table_h, I2, rscale,
-                                  rscale_is_int, rscale_i, acc, sum_r2, n_val, WeightLut{});
+          accumulate_point<kWeighted>(wc, rec, tab_x - xlo, table_w, tab_y, table_h, I2, rscale,
+                                      rscale_is_int, rscale_i, acc, sum_r2, n_val, lut);
           rec = rec_next;
           i = inext;
         }
@@ -404,8 +446,13 @@ int launch_shard_fused(const Geom& g, const Pools& p, ShardState* st, ShardFused
   if (std::max(tw, th) <= 1024) tw = th = 1024;
   else if (std::max(tw, th) <= 2048) tw = th = 2048;
   const size_t smem = sizeof(double) * 3 * (size_t)(tw + th);
-  static size_t smem_cache[kMaxDevices];  // one per kernel instantiation and device
-  if (!ensure_dynamic_smem(shard_fused_kernel, smem, smem_cache)) return -1;
+  const bool huber = g.weight_mode == UWT_WEIGHT_HUBER;
+  const void* kernel = huber ? (const void*)shard_fused_kernel<true>
+                             : (const void*)shard_fused_kernel<false>;
+  static size_t smem_cache[2][kMaxDevices];  // one per kernel instantiation and device
+  if (huber ? !ensure_dynamic_smem(shard_fused_kernel<true>, smem, smem_cache[1])
+            : !ensure_dynamic_smem(shard_fused_kernel<false>, smem, smem_cache[0]))
+    return -1;
   // cooperative launch: all CTAs must be co-resident (they wait on each other); grid <= 0 asks
   // for every CTA the device can hold at once (two per SM: twice the warps to hide the point
   // loop's latency)
@@ -413,7 +460,12 @@ int launch_shard_fused(const Geom& g, const Pools& p, ShardState* st, ShardFused
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_fused_kernel, kShardThreads, smem);
+    if (huber)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_fused_kernel<true>,
+                                                    kShardThreads, smem);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_fused_kernel<false>,
+                                                    kShardThreads, smem);
     grid = std::max(1, std::min(sms * std::max(per_sm, 1), kShardMaxGrid));
   }
   static unsigned poll_ns = 0;
@@ -424,8 +476,8 @@ int launch_shard_fused(const Geom& g, const Pools& p, ShardState* st, ShardFused
   }
   void* args[] = {(void*)&g, (void*)&p, (void*)&st, (void*)&ctl, (void*)&mine, (void*)&partials,
                   (void*)&tw, (void*)&th, (void*)&poll_ns};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)shard_fused_kernel, dim3(grid),
-                                              dim3(kShardThreads), args, smem, stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kShardThreads), args, smem,
+                                              stream);
   return e == cudaSuccess ? 1 : -1;
 }
 
