@@ -33,7 +33,8 @@ def test_committed_soak_records_are_clean():
                          # the end-of-round kernels (16384-record tasks, late-sweep rule, rewritten
                          # scatter): every sweep at 64 problems per call, final poses at 256
                          ("parity_soak_r02s_traced.json", 8192),
-                         ("parity_soak_r02s_batch256.json", 16384)):
+                         ("parity_soak_r02s_batch256.json", 16384),
+                         ("parity_soak_r02v_50k.json", 50048)):
         with open(os.path.join(ROOT, "profiles", name)) as f:
             j = json.load(f)
         assert j["tracks"] == tracks and j["sweeps"] > 10 * tracks
